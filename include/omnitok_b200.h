@@ -1,0 +1,148 @@
+/*
+ * omnitok_b200 -- C ABI of the B200 (sm_100a) kernels behind OmniTokenizer_VQGAN.encode/decode.
+ *
+ * The reference (FoundationVision/OmniTokenizer) has no FFI of its own: its boundary is the
+ * Python module API of OmniTokenizer_VQGAN (OmniTokenizer/omnitokenizer.py:63-413).  Each entry
+ * point below replaces one group of torch library calls on that path; the reference call site
+ * it stands in for is cited next to it (paths relative to /root/reference/OmniTokenizer/).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (fp32 unless noted); nothing is
+ *     allocated or retained; outputs may not alias inputs unless stated.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return 0 on success, negative on error (OMT_E_*); omt_last_error() gives the message
+ *     (thread-local).  There is NO CPU fallback: a non-sm_100 device returns OMT_E_ARCH.
+ *   - activations live in ONE canonical layout  X[B][T'][N][C]  (C fastest; identical to the
+ *     reference's "(b t) (h w) d" tensor).  "rows" are (b,t',n) triples, M = B*T'*N.
+ *   - a "row map" (seg, seg_stride, seg_off) maps logical GEMM row r to physical row
+ *     (r / seg) * seg_stride + seg_off + (r % seg); seg <= 0 means identity.  It is how the
+ *     first-frame / rest-frames patch matrices address the canonical buffer without a concat.
+ */
+#ifndef OMNITOK_B200_H_
+#define OMNITOK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMT_ABI_VERSION 1
+
+#define OMT_OK 0
+#define OMT_E_ARG (-1)    /* bad shape / alignment / null pointer */
+#define OMT_E_ARCH (-2)   /* device is not sm_100 */
+#define OMT_E_CUDA (-3)   /* a CUDA runtime call failed */
+#define OMT_E_UNSUPPORTED (-4)
+
+typedef void* omt_stream_t;
+
+int omt_abi_version(void);
+const char* omt_last_error(void);
+/* sm count / compute capability of the current device */
+int omt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* GEMM epilogue selectors */
+#define OMT_EPI_NONE 0
+#define OMT_EPI_GEGLU 1   /* packed columns (2j, 2j+1) = (value, gate): C[:, j] = gelu_erf(gate) * value */
+
+/* GEMM math selectors */
+#define OMT_MATH_FP32 0      /* CUDA-core FFMA, exact fp32 (parity anchor) */
+#define OMT_MATH_3XTF32 1    /* tcgen05 kind::tf32, error-compensated hi/lo split, fp32 accumulate in TMEM */
+#define OMT_MATH_TF32 2      /* tcgen05 kind::tf32 single pass (throughput mode; NOT index-exact) */
+
+/* C[M, N] = A[M, K] . W[N, K]^T (+ bias[N]) (+ residual[M, N]); nn.Linear everywhere on the path:
+ * attention.py:411 (to_q / to_kv), :486 (to_out), :271/:288 (window qkv / proj), :164/:167 (FF),
+ * omnitokenizer.py:809,819 (patch embed), :1007,1013 (to_pixels).
+ * W must be allocated with rows padded up to a multiple of 128 (zero rows); K % 8 == 0 (fp32 path)
+ * or K % 32 == 0 (tcgen05 paths).  With OMT_EPI_GEGLU, N counts packed columns and C has N/2 columns.
+ * residual may alias C (same ld): out-of-place is not required.  For OMT_MATH_3XTF32 `W` must be the
+ * tf32-rounded (round-to-nearest, low 13 mantissa bits zero) high part of the weight and `W_lo` the
+ * exact remainder (same shape); W_lo is ignored (may be NULL) for FP32 / TF32. */
+int omt_linear(const float* A, int lda, int a_seg, int a_seg_stride, int a_seg_off,
+               const float* W, const float* W_lo,
+               float* C, int ldc, int c_seg, int c_seg_stride, int c_seg_off,
+               int M, int N, int K,
+               const float* bias, const float* residual, int ldr,
+               int epilogue, int math, omt_stream_t stream);
+
+/* y[r,:] = (x[r,:] - mean) * rstd * w + b over C channels (C % 4 == 0, C <= 1024); b may be NULL.
+ * attention.py:73-80 (LayerNorm, beta buffer), :163 (nn.LayerNorm in FeedForward), :688 (norm_out).
+ * x may alias y.  (seg, seg_stride, seg_off) is a row map applied to BOTH x and y (patch embed:
+ * the first-frame and rest-frames rows of X carry different LayerNorm weights, omnitokenizer.py:811,821). */
+int omt_layernorm(const float* x, int ldx, float* y, int ldy, const float* w, const float* b,
+                  int M, int C, float eps, int seg, int seg_stride, int seg_off, omt_stream_t stream);
+
+/* Patch gather + LayerNorm (omnitokenizer.py:806-808 / :814-817: Rearrange + nn.LayerNorm).
+ * video (B, Cin, T, H, W) fp32 contiguous.  first=1: frame 0, rows (b,h,w), features (c,p1,p2);
+ * first=0: frames 1.., rows (b,t,h,w), features (c,pt,p1,p2).  A is [rows, K] dense. */
+int omt_patchify_ln(const float* video, float* A, const float* ln_w, const float* ln_b,
+                    int B, int Cin, int T, int H, int W, int p, int pt, int first, float eps,
+                    omt_stream_t stream);
+
+/* Inverse Rearrange of to_pixels (omnitokenizer.py:1008 / :1015): P [rows, K] -> video (B,Cin,T,H,W). */
+int omt_unpatchify(const float* P, float* video, int B, int Cin, int T, int H, int W, int p, int pt,
+                   int first, omt_stream_t stream);
+
+/* PEG (attention.py:298-338) + residual: y[r,:] = x[r,:] + bias + sum_k w[k,:] * x[nbr[r % rows_per_b, k] , :]
+ * nbr: int32 [rows_per_b, 27] canonical neighbour rows inside one batch element, -1 = zero padding
+ * (the spatial stencil or the reference's literally-reshaped "scrambled" temporal one, built by the host);
+ * w27: weights repacked [27, C]. */
+int omt_peg(const float* x, float* y, const float* w27, const float* bias, const int32_t* nbr,
+            int B, int rows_per_b, int C, omt_stream_t stream);
+
+/* In-place rope + l2norm + per-dim scale on q and k (attention.py:417-421, :435-437).
+ * q[M, heads*64] (ld ldq), k likewise; cos/sin [N, 32] or NULL (no rope; temporal blocks);
+ * the rope position of row r is r % N. */
+int omt_qk_prep(float* q, int ldq, float* k, int ldk, const float* q_scale, const float* k_scale,
+                const float* rope_cos, const float* rope_sin, int M, int N, int heads,
+                omt_stream_t stream);
+
+/* Full (non-causal) attention over n_seq sequences of N contiguous canonical rows, head dim 64:
+ * o = softmax(scale * q k^T) v   (attention.py:451, SDPA branch: no additive bias).  N % 64 == 0. */
+int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                     float* o, int ldo, int n_seq, int N, int heads, float scale, omt_stream_t stream);
+
+/* 8x8 (ws x ws, ws*ws == 64) window attention with relative position bias (attention.py:254-286):
+ * o = softmax(scale * q k^T + bias[head]) v within each window of the (h, w) token grid.
+ * bias: [heads, 64, 64] already gathered from the 225-entry table. */
+int omt_attn_window(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                    float* o, int ldo, const float* bias, int n_frames, int h, int w, int ws, int heads,
+                    float scale, omt_stream_t stream);
+
+/* Temporal attention: for every (b, n) a sequence over t' (rows b*T*N + t*N + n), optional causal
+ * mask (attention.py:451 is_causal); 1 <= T <= 17. */
+int omt_attn_temporal(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                      float* o, int ldo, int B, int T, int N, int heads, float scale, int causal,
+                      omt_stream_t stream);
+
+/* pre_vq_conv (omnitokenizer.py:144-154) [+ F.normalize(dim=channels) :251-252]:
+ * z[M, cd] = x[M, C] . Wt^T + b, cd in {8, 16}; l2 != 0 divides each row by max(||z||, 1e-12). */
+int omt_pre_vq(const float* x, int ldx, const float* Wt, const float* b, float* z, int M, int C, int cd,
+               int l2, omt_stream_t stream);
+
+/* Codebook.forward nearest-neighbour search (modules/codebook.py:82-86), cd == 8:
+ * d[n,k] = (sum z^2 - 2 z.E_k) + sum E_k^2 in that association, idx = first argmin.
+ * e2: [n_codes] precomputed sum E^2.  workspace: >= 4 * M * 8 bytes.  Also accumulates
+ * counts[n_codes] (int32, caller zeroes) -- the fixed-size replacement of torch.unique (:65). */
+int omt_vq_search(const float* z, const float* E, const float* e2, int M, int n_codes,
+                  int64_t* idx, int32_t* counts, void* workspace, omt_stream_t stream);
+
+/* Decode-side lookup: F.embedding gather (omnitokenizer.py:270) + post_vq_conv Linear(cd, C) (:156-160).
+ * If idx != NULL rows come from E[idx[r]]; else from zc[M, cd].  X[M, C] = row . Wt^T + b.
+ * When z_st_from != NULL (forward(): straight-through, codebook.py:120) the row is (E[idx]-z)+z and is
+ * also written to zq_out[M, cd] (may be NULL). */
+int omt_post_vq(const int64_t* idx, const float* E, const float* zc, const float* z_st_from,
+                float* zq_out, const float* Wt, const float* b, float* X, int M, int C, int cd,
+                omt_stream_t stream);
+
+/* Tuning knobs (process-wide).  "tc_block_n" = 128 | 256: tile-N of the tcgen05 GEMM. */
+int omt_set_option(const char* name, int value);
+
+/* hi/lo split used by the tcgen05 3xTF32 path: lo = x - tf32_trunc(x) (elementwise, n % 4 == 0). */
+int omt_split_lo(const float* x, float* lo, int64_t n, omt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNITOK_B200_H_ */

@@ -1,0 +1,107 @@
+"""ctypes binding of libomnitok_b200.so (the C ABI in include/omnitok_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised.  Tensors are passed as raw device pointers; every call runs on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p, POINTER
+
+import torch
+
+_LIB_NAME = "libomnitok_b200.so"
+_lib = None
+
+EPI_NONE, EPI_GEGLU = 0, 1
+MATH_FP32, MATH_3XTF32, MATH_TF32 = 0, 1, 2
+
+# name -> (restype, argtypes); mirrors include/omnitok_b200.h one to one
+SIGNATURES = {
+    "omt_abi_version": (c_int, []),
+    "omt_last_error": (c_char_p, []),
+    "omt_device_info": (c_int, [POINTER(c_int)] * 3),
+    "omt_set_option": (c_int, [c_char_p, c_int]),
+    "omt_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                           c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "omt_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int,
+                              c_int, c_void_p]),
+    "omt_patchify_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_float, c_void_p]),
+    "omt_unpatchify": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "omt_peg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "omt_qk_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                            c_int, c_void_p]),
+    "omt_attn_spatial": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_float, c_void_p]),
+    "omt_attn_window": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "omt_attn_temporal": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_int, c_float, c_int, c_void_p]),
+    "omt_pre_vq": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "omt_vq_search": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "omt_post_vq": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p]),
+    "omt_split_lo": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+}
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built (see __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` (or `make -C omnitokenizer_b200/csrc`). There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.omt_abi_version() != 1:
+        raise RuntimeError("libomnitok_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke an entry point on torch's current CUDA stream; tensors are converted to pointers."""
+    lib = load()
+    conv = [_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a for a in args]
+    rc = getattr(lib, name)(*conv, _stream())
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.omt_last_error().decode()}")
+
+
+def set_option(name: str, value: int):
+    lib = load()
+    rc = lib.omt_set_option(name.encode(), int(value))
+    if rc != 0:
+        raise RuntimeError(f"omt_set_option({name}) failed: {lib.omt_last_error().decode()}")
+
+
+def device_info():
+    lib = load()
+    a, b, c = c_int(), c_int(), c_int()
+    rc = lib.omt_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    if rc != 0:
+        raise RuntimeError(lib.omt_last_error().decode())
+    return a.value, b.value, c.value

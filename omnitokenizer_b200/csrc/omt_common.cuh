@@ -1,0 +1,70 @@
+// Shared helpers for the omnitok_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/omnitok_b200.h"
+
+namespace omt {
+
+void set_error(const char* fmt, ...);
+int check_device();   // OMT_OK when the current device is sm_100; caches per device
+int sm_count();
+
+#define OMT_REQUIRE(cond, ...)                  \
+  do {                                          \
+    if (!(cond)) {                              \
+      omt::set_error(__VA_ARGS__);              \
+      return OMT_E_ARG;                         \
+    }                                           \
+  } while (0)
+
+#define OMT_CUDA(call)                                                            \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) {                                                     \
+      omt::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),     \
+                     __FILE__, __LINE__);                                         \
+      return OMT_E_CUDA;                                                          \
+    }                                                                             \
+  } while (0)
+
+#define OMT_ENTER()                      \
+  do {                                   \
+    int rc__ = omt::check_device();      \
+    if (rc__ != OMT_OK) return rc__;     \
+  } while (0)
+
+#define OMT_LAUNCH_CHECK() OMT_CUDA(cudaGetLastError())
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// logical GEMM row -> physical row (see include/omnitok_b200.h)
+__host__ __device__ __forceinline__ long long map_row(int r, int seg, int seg_stride, int seg_off) {
+  if (seg <= 0) return r;
+  return (long long)(r / seg) * seg_stride + seg_off + (r % seg);
+}
+
+struct GemmArgs {
+  const float* A; int lda; int a_seg, a_seg_stride, a_seg_off;
+  const float* W;
+  float* C; int ldc; int c_seg, c_seg_stride, c_seg_off;
+  int M, N, K;
+  const float* bias; const float* residual; int ldr;
+};
+
+}  // namespace omt

@@ -1,0 +1,420 @@
+// Row-wise / HBM-bound kernels of the OmniTokenizer encode/decode path:
+// LayerNorm, patch gather+LN, un-patchify, PEG gather-stencil, rope+l2norm+scale.
+// All of them stream the canonical X[B][T'][N][C] buffer once with 16-byte accesses.
+#include "omt_common.cuh"
+#include <string.h>
+
+namespace omt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_dev_ok[64];   // 0 unknown, 1 ok, -1 bad
+static int g_sms[64];
+
+int check_device() {
+  int dev = 0;
+  OMT_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return OMT_E_ARG; }
+  if (g_dev_ok[dev] == 0) {
+    cudaDeviceProp p;
+    OMT_CUDA(cudaGetDeviceProperties(&p, dev));
+    g_sms[dev] = p.multiProcessorCount;
+    g_dev_ok[dev] = (p.major == 10) ? 1 : -1;
+  }
+  if (g_dev_ok[dev] < 0) {
+    set_error("omnitok_b200 kernels are built for sm_100a only (no fallback path)");
+    return OMT_E_ARCH;
+  }
+  return OMT_OK;
+}
+
+int sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64 && g_sms[dev] > 0) ? g_sms[dev] : 148;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, whole row in registers (C <= 1024), two-pass statistics.
+// ------------------------------------------------------------------------------------------
+template <int NV>   // float4 chunks per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx,
+                                                        float* __restrict__ y, int ldy,
+                                                        const float* __restrict__ w,
+                                                        const float* __restrict__ b, int M, int C,
+                                                        float eps, int seg, int seg_stride, int seg_off) {
+  const int lane = threadIdx.x & 31;
+  const int lrow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (lrow >= M) return;
+  const long long row = map_row(lrow, seg, seg_stride, seg_off);
+  const float* xr = x + (size_t)row * ldx;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < C) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < C) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+  float* yr = y + (size_t)row * ldy;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < C) {
+      const float4 g = *reinterpret_cast<const float4*>(w + c);
+      float4 o;
+      o.x = v[i].x * rstd * g.x; o.y = v[i].y * rstd * g.y;
+      o.z = v[i].z * rstd * g.z; o.w = v[i].w * rstd * g.w;
+      if (b != nullptr) {
+        const float4 bb = *reinterpret_cast<const float4*>(b + c);
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+      }
+      *reinterpret_cast<float4*>(yr + c) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Patch gather + LayerNorm.  One warp per patch row; K = Cin*p*p (first frame) or Cin*pt*p*p.
+// Feature f = ((c*PT + dt)*p + p1)*p + p2 ; p2 is contiguous in the video (p % 4 == 0).
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restrict__ video,
+                                                          float* __restrict__ A,
+                                                          const float* __restrict__ lw,
+                                                          const float* __restrict__ lb, int rows,
+                                                          int Cin, int T, int H, int W, int p, int pt,
+                                                          int first, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int hh = H / p, ww = W / p;
+  const int PT = first ? 1 : pt;
+  const int K = Cin * PT * p * p;
+  int r = row;
+  const int wi = r % ww; r /= ww;
+  const int hi = r % hh; r /= hh;
+  int ti = 0;
+  if (!first) { const int tn = (T - 1) / pt; ti = r % tn; r /= tn; }
+  const int bi = r;
+  const int t0 = first ? 0 : 1 + ti * pt;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int f = (i * 32 + lane) * 4;
+    if (f < K) {
+      const int p2 = f % p;
+      const int p1 = (f / p) % p;
+      const int dt = (f / (p * p)) % PT;
+      const int c = f / (p * p * PT);
+      const size_t off = ((((size_t)bi * Cin + c) * T + (t0 + dt)) * H + (hi * p + p1)) * W + wi * p + p2;
+      v[i] = *reinterpret_cast<const float4*>(video + off);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / (float)K;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int f = (i * 32 + lane) * 4;
+    if (f < K) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + eps);
+  float* ar = A + (size_t)row * K;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int f = (i * 32 + lane) * 4;
+    if (f < K) {
+      const float4 g = *reinterpret_cast<const float4*>(lw + f);
+      const float4 bb = *reinterpret_cast<const float4*>(lb + f);
+      float4 o;
+      o.x = v[i].x * rstd * g.x + bb.x; o.y = v[i].y * rstd * g.y + bb.y;
+      o.z = v[i].z * rstd * g.z + bb.z; o.w = v[i].w * rstd * g.w + bb.w;
+      *reinterpret_cast<float4*>(ar + f) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict__ P,
+                                                         float* __restrict__ video, long long total4,
+                                                         int Cin, int T, int H, int W, int p, int pt,
+                                                         int first) {
+  const int hh = H / p, ww = W / p;
+  const int PT = first ? 1 : pt;
+  const int K4 = Cin * PT * p * p / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % K4) * 4;
+    int r = (int)(i / K4);
+    const int wi = r % ww; r /= ww;
+    const int hi = r % hh; r /= hh;
+    int ti = 0;
+    if (!first) { const int tn = (T - 1) / pt; ti = r % tn; r /= tn; }
+    const int bi = r;
+    const int t0 = first ? 0 : 1 + ti * pt;
+    const int p2 = f % p;
+    const int p1 = (f / p) % p;
+    const int dt = (f / (p * p)) % PT;
+    const int c = f / (p * p * PT);
+    const size_t off = ((((size_t)bi * Cin + c) * T + (t0 + dt)) * H + (hi * p + p1)) * W + wi * p + p2;
+    *reinterpret_cast<float4*>(video + off) = *reinterpret_cast<const float4*>(P + i * 4);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PEG: y = x + bias + sum_k w[k] * x[nbr[k]].  Block = C/4 threads (one float4 channel group
+// each), loops over ROWS consecutive rows; the 27 x C weight table sits in shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int PEG_ROWS = 16;
+
+__global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                  const float* __restrict__ w27,
+                                                  const float* __restrict__ bias,
+                                                  const int32_t* __restrict__ nbr, int rows_per_b,
+                                                  int C, long long M) {
+  extern __shared__ float4 wsm[];   // [27][C/4]
+  __shared__ int32_t nsm[PEG_ROWS][27];
+  const int c4 = threadIdx.x;       // channel group
+  const int C4 = C >> 2;
+  for (int i = threadIdx.x; i < 27 * C4; i += blockDim.x)
+    wsm[i] = reinterpret_cast<const float4*>(w27)[i];
+  const long long r0 = (long long)blockIdx.x * PEG_ROWS;
+  for (int i = threadIdx.x; i < PEG_ROWS * 27; i += blockDim.x) {
+    const long long r = r0 + i / 27;
+    nsm[i / 27][i % 27] = (r < M) ? nbr[(r % rows_per_b) * 27 + (i % 27)] : -1;
+  }
+  __syncthreads();
+  if (c4 >= C4) return;
+  const float4 bb = reinterpret_cast<const float4*>(bias)[c4];
+  for (int rr = 0; rr < PEG_ROWS; ++rr) {
+    const long long r = r0 + rr;
+    if (r >= M) break;
+    const long long base = (r / rows_per_b) * rows_per_b;
+    const float4 xv = reinterpret_cast<const float4*>(x + r * C)[c4];
+    float4 acc = bb;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const int n = nsm[rr][k];
+      if (n >= 0) {
+        const float4 nv = __ldg(reinterpret_cast<const float4*>(x + (base + n) * C) + c4);
+        const float4 wv = wsm[k * C4 + c4];
+        acc.x = fmaf(nv.x, wv.x, acc.x); acc.y = fmaf(nv.y, wv.y, acc.y);
+        acc.z = fmaf(nv.z, wv.z, acc.z); acc.w = fmaf(nv.w, wv.w, acc.w);
+      }
+    }
+    acc.x += xv.x; acc.y += xv.y; acc.z += xv.z; acc.w += xv.w;
+    reinterpret_cast<float4*>(y + r * C)[c4] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// rope + l2norm + scale, in place on q and k.  One warp per row; lane l owns the complex pair
+// (2l, 2l+1) of every head.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void qk_prep_one(float* p, const float2 cs, bool rope, const float2 sc) {
+  float2 v = *reinterpret_cast<float2*>(p);
+  if (rope) {
+    const float a = v.x * cs.x - v.y * cs.y;
+    const float b = v.x * cs.y + v.y * cs.x;
+    v.x = a; v.y = b;
+  }
+  const float ss = warp_sum(v.x * v.x + v.y * v.y);
+  const float den = fmaxf(sqrtf(ss), 1e-12f);
+  v.x = v.x / den * sc.x;
+  v.y = v.y / den * sc.y;
+  *reinterpret_cast<float2*>(p) = v;
+}
+
+__global__ void __launch_bounds__(256) qk_prep_kernel(float* __restrict__ q, int ldq,
+                                                      float* __restrict__ k, int ldk,
+                                                      const float* __restrict__ qs,
+                                                      const float* __restrict__ ks,
+                                                      const float* __restrict__ rc,
+                                                      const float* __restrict__ rs, int M, int N,
+                                                      int heads) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const bool rope = rc != nullptr;
+  float2 cs = make_float2(1.f, 0.f);
+  if (rope) {
+    const int pos = row % N;
+    cs.x = rc[pos * 32 + lane];
+    cs.y = rs[pos * 32 + lane];
+  }
+  const float2 sq = *reinterpret_cast<const float2*>(qs + 2 * lane);
+  const float2 sk = *reinterpret_cast<const float2*>(ks + 2 * lane);
+  for (int h = 0; h < heads; ++h) {
+    qk_prep_one(q + (size_t)row * ldq + h * 64 + 2 * lane, cs, rope, sq);
+    qk_prep_one(k + (size_t)row * ldk + h * 64 + 2 * lane, cs, rope, sk);
+  }
+}
+
+__global__ void split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    float4 o;
+    o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    lo[i] = o;
+  }
+}
+
+}  // namespace omt
+
+using namespace omt;
+
+extern "C" int omt_abi_version(void) { return OMT_ABI_VERSION; }
+extern "C" const char* omt_last_error(void) { return omt::g_err; }
+
+extern "C" int omt_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  OMT_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  OMT_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sms) *sms = p.multiProcessorCount;
+  if (major) *major = p.major;
+  if (minor) *minor = p.minor;
+  return OMT_OK;
+}
+
+extern "C" int omt_layernorm(const float* x, int ldx, float* y, int ldy, const float* w, const float* b,
+                             int M, int C, float eps, int seg, int seg_stride, int seg_off,
+                             omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(x && y && w, "omt_layernorm: null pointer");
+  OMT_REQUIRE(M >= 0 && C > 0 && C % 4 == 0 && C <= 1024, "omt_layernorm: C=%d must be a multiple of 4, <= 1024", C);
+  OMT_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C, "omt_layernorm: bad leading dims");
+  if (M == 0) return OMT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nv = (C / 4 + 31) / 32;
+  dim3 grid((M + 7) / 8), block(256);
+  switch (nv) {
+    case 1: layernorm_kernel<1><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
+    case 2: layernorm_kernel<2><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
+    case 3: layernorm_kernel<3><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
+    case 4: layernorm_kernel<4><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
+    default: layernorm_kernel<8><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
+  }
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
+extern "C" int omt_patchify_ln(const float* video, float* A, const float* ln_w, const float* ln_b, int B,
+                               int Cin, int T, int H, int W, int p, int pt, int first, float eps,
+                               omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(video && A && ln_w && ln_b, "omt_patchify_ln: null pointer");
+  OMT_REQUIRE(p % 4 == 0 && H % p == 0 && W % p == 0, "omt_patchify_ln: patch %d must be a multiple of 4 dividing %dx%d", p, H, W);
+  OMT_REQUIRE(first || (T > 1 && (T - 1) % pt == 0), "omt_patchify_ln: (T-1) %% pt != 0");
+  const int PT = first ? 1 : pt;
+  const int K = Cin * PT * p * p;
+  OMT_REQUIRE(K <= 1024, "omt_patchify_ln: patch vector %d > 1024", K);
+  const long long rows = (long long)B * (first ? 1 : (T - 1) / pt) * (H / p) * (W / p);
+  if (rows == 0) return OMT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((rows + 7) / 8)), block(256);
+  const int nv = (K / 4 + 31) / 32;
+  if (nv <= 2)
+    patchify_ln_kernel<2><<<grid, block, 0, st>>>(video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps);
+  else if (nv <= 6)
+    patchify_ln_kernel<6><<<grid, block, 0, st>>>(video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps);
+  else
+    patchify_ln_kernel<8><<<grid, block, 0, st>>>(video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps);
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
+extern "C" int omt_unpatchify(const float* P, float* video, int B, int Cin, int T, int H, int W, int p,
+                              int pt, int first, omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(P && video, "omt_unpatchify: null pointer");
+  OMT_REQUIRE(p % 4 == 0 && H % p == 0 && W % p == 0, "omt_unpatchify: bad patch size");
+  OMT_REQUIRE(first || (T > 1 && (T - 1) % pt == 0), "omt_unpatchify: (T-1) %% pt != 0");
+  const int PT = first ? 1 : pt;
+  const long long rows = (long long)B * (first ? 1 : (T - 1) / pt) * (H / p) * (W / p);
+  const long long total4 = rows * (Cin * PT * p * p / 4);
+  if (total4 == 0) return OMT_OK;
+  long long blocks = (total4 + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  unpatchify_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, video, total4, Cin, T, H, W, p, pt, first);
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
+extern "C" int omt_peg(const float* x, float* y, const float* w27, const float* bias, const int32_t* nbr,
+                       int B, int rows_per_b, int C, omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(x && y && w27 && bias && nbr, "omt_peg: null pointer");
+  OMT_REQUIRE(x != y, "omt_peg: in-place is not supported (stencil)");
+  OMT_REQUIRE(C % 4 == 0 && C / 4 <= 128, "omt_peg: C=%d unsupported (need C %% 4 == 0, C <= 512)", C);
+  const long long M = (long long)B * rows_per_b;
+  if (M == 0) return OMT_OK;
+  static bool attr_set = false;
+  const size_t smem = (size_t)27 * C * sizeof(float);
+  if (!attr_set) {
+    OMT_CUDA(cudaFuncSetAttribute(peg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 27 * 512 * 4));
+    attr_set = true;
+  }
+  const unsigned blocks = (unsigned)((M + PEG_ROWS - 1) / PEG_ROWS);
+  peg_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(x, y, w27, bias, nbr, rows_per_b, C, M);
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
+extern "C" int omt_qk_prep(float* q, int ldq, float* k, int ldk, const float* q_scale, const float* k_scale,
+                           const float* rope_cos, const float* rope_sin, int M, int N, int heads,
+                           omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(q && k && q_scale && k_scale, "omt_qk_prep: null pointer");
+  OMT_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "omt_qk_prep: cos/sin must both be given");
+  OMT_REQUIRE(ldq % 2 == 0 && ldk % 2 == 0 && N > 0, "omt_qk_prep: bad leading dims");
+  if (M == 0) return OMT_OK;
+  qk_prep_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, q_scale, k_scale, rope_cos,
+                                                                rope_sin, M, N, heads);
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
+extern "C" int omt_split_lo(const float* x, float* lo, int64_t n, omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(x && lo && n % 4 == 0, "omt_split_lo: n must be a multiple of 4");
+  if (n == 0) return OMT_OK;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  split_lo_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n / 4);
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}

@@ -1,0 +1,302 @@
+"""Kernel orchestration for OmniTokenizer_VQGAN.encode / decode / forward on one B200.
+
+The engine owns (a) the packed device copies of the checkpoint in kernel layouts and (b) the
+per-shape workspace; every arithmetic step is a call into libomnitok_b200.so (see
+include/omnitok_b200.h).  torch is used for device memory, streams and a handful of
+O(codebook)-sized reductions (usage statistics) -- never for the per-token math.
+
+Activations stay in ONE canonical buffer X[B][T'][N][C] for the whole network.  The reference's
+four rearrange copies between spatial and temporal blocks (omnitokenizer.py:891,902,907,1072,1081)
+do not exist here: spatial kernels read rows contiguously, temporal kernels stride by N, window
+attention and both PEG variants go through index maps.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _cabi
+from . import layout as L
+
+MATH_MODES = {"fp32": _cabi.MATH_FP32, "3xtf32": _cabi.MATH_3XTF32, "tf32": _cabi.MATH_TF32}
+
+
+def default_math() -> str:
+    return os.environ.get("OMT_MATH", "3xtf32").lower()
+
+
+class PackedLinear:
+    """nn.Linear weight in GEMM layout: rows padded to 128, K padded, optional tf32 hi/lo split."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], device, math: int,
+                 k_pad: Optional[int] = None, geglu: Optional[Tuple[int, int]] = None):
+        w = weight.detach().to(device=device, dtype=torch.float32)
+        if geglu is not None:
+            inner, ku = geglu
+            w = L.pack_geglu(w, inner, ku)
+        self.n = w.shape[0]
+        if k_pad is not None:
+            w = L.pad_cols(w, k_pad)
+        self.k = w.shape[1]
+        w = L.pad_rows(w, 128)
+        if math == _cabi.MATH_3XTF32:
+            hi = L.tf32_round(w)
+            self.w, self.w_lo = hi, (w - hi).contiguous()
+        else:
+            self.w, self.w_lo = w, None
+        self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.math = math
+
+
+class Workspace:
+    def __init__(self, device, M: int, C: int, ku: int, kmax: int, cd: int):
+        f = dict(device=device, dtype=torch.float32)
+        self.M = M
+        self.X = torch.empty(M, C, **f)
+        self.Y = torch.empty(M, C, **f)
+        self.XN = torch.empty(M, C, **f)
+        self.QKV = torch.empty(M, 3 * C, **f)
+        self.O = torch.empty(M, C, **f)
+        self.U = torch.empty(M, ku, **f)
+        self.P = torch.empty(M, kmax, **f)       # patch matrix (pixels side), rows x K
+        self.z = torch.empty(M, cd, **f)
+        self.idx = torch.empty(M, device=device, dtype=torch.int64)
+        self.counts = torch.zeros(8192, device=device, dtype=torch.int32)
+        self.vqws = torch.empty(4 * M * 2, **f)
+
+
+class Engine:
+    def __init__(self, model, device: torch.device, math: Optional[str] = None):
+        _cabi.load()
+        self.device = device
+        self.math_name = (math or default_math()).lower()
+        if self.math_name not in MATH_MODES:
+            raise ValueError(f"unknown OMT_MATH mode {self.math_name!r}; choose from {sorted(MATH_MODES)}")
+        self.math = MATH_MODES[self.math_name]
+        a = model.args
+        self.C = a.embedding_dim
+        self.heads, self.dh = a.heads, a.dim_head
+        if self.C != 512 or self.dh != 64 or self.heads * self.dh != self.C:
+            raise NotImplementedError("omnitok_b200 kernels are specialised for embedding_dim=512, heads x dim_head = 8 x 64")
+        self.p, self.pt, self.cin = a.patch_size, a.temporal_patch_size, a.image_channels
+        self.ws = a.twod_window_size
+        self.causal_attn = bool(a.causal_in_temporal_transformer)
+        self.causal_peg = bool(a.causal_in_peg)
+        self.rope = a.spatial_pos == "rope"
+        self.use_vae = bool(model.use_vae)
+        self.cd = a.codebook_dim
+        self.l2 = bool(a.l2_code)
+        if a.attn_dropout != 0 or a.ff_dropout != 0:
+            raise NotImplementedError("non-zero dropout reaches SDPA even in eval in the reference (attention.py:451); rejected")
+        self._ws: Dict[Tuple, Workspace] = {}
+        self._tables: Dict[Tuple, torch.Tensor] = {}
+        sd = {k: v for k, v in model.state_dict().items()}
+        self._pack(sd, a)
+
+    # ------------------------------------------------------------------ packing
+    def _pack(self, sd, a):
+        dev, m = self.device, self.math
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        self.inner = sd["encoder.enc_spatial_transformer.layers.0.3.4.weight"].shape[1]
+        self.ku = L.round_up(self.inner, 32)
+
+        def lin(name, bias=True, **kw):
+            return PackedLinear(sd[name + ".weight"], sd.get(name + ".bias") if bias else None, dev, m, **kw)
+
+        def t_layer(lp):
+            d = {"kind": "t"}
+            d["peg_w"] = f32(sd[lp + ".0.dsconv.weight"].reshape(self.C, 27).t())      # [27, C]
+            d["peg_b"] = f32(sd[lp + ".0.dsconv.bias"])
+            ap = lp + ".1"
+            d["norm_g"], d["norm_b"] = f32(sd[ap + ".norm.gamma"]), f32(sd[ap + ".norm.beta"])
+            d["q_scale"], d["k_scale"] = f32(sd[ap + ".q_scale"]), f32(sd[ap + ".k_scale"])
+            d["to_q"] = lin(ap + ".to_q", bias=False)
+            d["to_kv"] = lin(ap + ".to_kv", bias=False)
+            d["to_out"] = lin(ap + ".to_out", bias=False)
+            ff(d, lp + ".3")
+            return d
+
+        def w_layer(lp):
+            d = {"kind": "w"}
+            ap = lp + ".1"
+            d["norm_g"], d["norm_b"] = f32(sd[ap + ".norm.gamma"]), f32(sd[ap + ".norm.beta"])
+            d["bias"] = L.window_bias(sd[ap + ".relative_position_bias_table"].detach().float().cpu(),
+                                      sd[ap + ".relative_position_index"].cpu(), self.ws).to(dev)
+            d["qkv"] = lin(ap + ".qkv", bias=False)
+            d["proj"] = lin(ap + ".proj")
+            ff(d, lp + ".3")
+            return d
+
+        def ff(d, fp):
+            d["ff_g"], d["ff_b"] = f32(sd[fp + ".0.weight"]), f32(sd[fp + ".0.bias"])
+            d["ff1"] = PackedLinear(sd[fp + ".1.weight"], None, dev, m, geglu=(self.inner, self.ku))
+            d["ff2"] = PackedLinear(sd[fp + ".4.weight"], None, dev, m, k_pad=self.ku)
+
+        def transformer(pre, block):
+            layers = []
+            for i, blk in enumerate(block):
+                if blk == "t":
+                    layers.append(t_layer(f"{pre}.layers.{i}"))
+                elif blk == "w":
+                    layers.append(w_layer(f"{pre}.layers.{i}"))
+                else:
+                    raise NotImplementedError(f"block type {blk!r}: pooling/upsampling blocks are outside the shipped configs")
+            return {"layers": layers, "out_g": f32(sd[pre + ".norm_out.gamma"]), "out_b": f32(sd[pre + ".norm_out.beta"])}
+
+        tb = "t" * a.temporal_depth
+        self.enc_spatial = transformer("encoder.enc_spatial_transformer", a.enc_block)
+        self.enc_temporal = transformer("encoder.enc_temporal_transformer", tb)
+        self.dec_temporal = transformer("decoder.dec_temporal_transformer", tb)
+        self.dec_spatial = transformer("decoder.dec_spatial_transformer", a.dec_block)
+
+        self.pe = {}
+        for key, pre in (("first", "encoder.to_patch_emb_first_frame"), ("rest", "encoder.to_patch_emb")):
+            self.pe[key] = dict(ln1_g=f32(sd[pre + ".1.weight"]), ln1_b=f32(sd[pre + ".1.bias"]), lin=lin(pre + ".2"),
+                                ln2_g=f32(sd[pre + ".3.weight"]), ln2_b=f32(sd[pre + ".3.bias"]))
+        self.px = {"first": lin("decoder.to_pixels_first_frame.0"), "rest": lin("decoder.to_pixels.0")}
+        self.pre_w, self.pre_b = f32(sd["pre_vq_conv.1.weight"]), f32(sd["pre_vq_conv.1.bias"])
+        self.post_w, self.post_b = f32(sd["post_vq_conv.1.weight"]), f32(sd["post_vq_conv.1.bias"])
+        E = sd["codebook.embeddings"].detach().float()
+        self.E = E.to(dev).contiguous()
+        # sum E^2 with the reference's own expression (modules/codebook.py:84), evaluated on the host
+        self.e2 = (E.cpu().t() ** 2).sum(dim=0).to(dev).contiguous()
+        self.n_codes = E.shape[0]
+
+    # ------------------------------------------------------------------ helpers
+    def _workspace(self, M: int) -> Workspace:
+        ws = self._ws.get(M)
+        if ws is None:
+            kmax = self.cin * self.pt * self.p * self.p
+            ws = Workspace(self.device, M, self.C, self.ku, kmax, max(self.cd, 16))
+            if ws.counts.numel() < self.n_codes:
+                ws.counts = torch.zeros(self.n_codes, device=self.device, dtype=torch.int32)
+            self._ws.clear()          # keep one shape resident
+            self._ws[M] = ws
+        return ws
+
+    def _table(self, key, fn):
+        t = self._tables.get(key)
+        if t is None:
+            t = fn()
+            t = tuple(x.to(self.device) for x in t) if isinstance(t, tuple) else t.to(self.device)
+            self._tables[key] = t
+        return t
+
+    def _linear(self, A, lda, lin: PackedLinear, C, ldc, M, *, a_map=(0, 0, 0), c_map=(0, 0, 0), residual=None,
+                ldr=0, epi=_cabi.EPI_NONE, bias=True):
+        _cabi.call("omt_linear", A, lda, a_map[0], a_map[1], a_map[2], lin.w, lin.w_lo, C, ldc, c_map[0], c_map[1],
+                   c_map[2], M, lin.n, lin.k, lin.bias if bias else None, residual, ldr, epi, lin.math)
+
+    def _ln(self, x, y, g, b, M, C=None, seg=(0, 0, 0)):
+        C = C or self.C
+        _cabi.call("omt_layernorm", x, C, y, C, g, b, M, C, 1e-5, seg[0], seg[1], seg[2])
+
+    # ------------------------------------------------------------------ transformer
+    def _transformer(self, tr, ws: Workspace, B, T, h, w, temporal: bool):
+        C, N, M = self.C, h * w, ws.M
+        q_ptr = ws.QKV.data_ptr()
+        k_ptr, v_ptr = q_ptr + C * 4, q_ptr + 2 * C * 4
+        ld3 = 3 * C
+        for lyr in tr["layers"]:
+            if lyr["kind"] == "t":
+                nbr = self._table(("peg", T, h, w, temporal, self.causal_peg),
+                                  lambda: L.peg_neighbour_table(T, h, w, temporal, self.causal_peg))
+                _cabi.call("omt_peg", ws.X, ws.Y, lyr["peg_w"], lyr["peg_b"], nbr, B, T * N, C)
+                ws.X, ws.Y = ws.Y, ws.X
+                self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
+                self._linear(ws.XN, C, lyr["to_q"], q_ptr, ld3, M)            # q from the normalised input
+                self._linear(ws.X, C, lyr["to_kv"], k_ptr, ld3, M)            # k, v from the RAW input (attention.py:407)
+                cos = sin = None
+                if (not temporal) and self.rope:
+                    cos, sin = self._table(("rope", N), lambda: L.rope_tables(N, self.dh))
+                _cabi.call("omt_qk_prep", q_ptr, ld3, k_ptr, ld3, lyr["q_scale"], lyr["k_scale"], cos, sin, M, N,
+                           self.heads)
+                if temporal:
+                    _cabi.call("omt_attn_temporal", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, ws.O, C, B, T, N, self.heads,
+                               8.0, int(self.causal_attn))
+                else:
+                    _cabi.call("omt_attn_spatial", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, ws.O, C, B * T, N, self.heads,
+                               8.0)
+                self._linear(ws.O, C, lyr["to_out"], ws.X, C, M, residual=ws.X, ldr=C)
+            else:
+                self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
+                self._linear(ws.XN, C, lyr["qkv"], q_ptr, ld3, M)
+                _cabi.call("omt_attn_window", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, ws.O, C, lyr["bias"], B * T, h, w,
+                           self.ws, self.heads, float(self.dh) ** -0.5)
+                self._linear(ws.O, C, lyr["proj"], ws.X, C, M, residual=ws.X, ldr=C)
+            self._ln(ws.X, ws.XN, lyr["ff_g"], lyr["ff_b"], M)
+            self._linear(ws.XN, C, lyr["ff1"], ws.U, self.ku, M, epi=_cabi.EPI_GEGLU)
+            self._linear(ws.U, self.ku, lyr["ff2"], ws.X, C, M, residual=ws.X, ldr=C)
+        self._ln(ws.X, ws.X, tr["out_g"], tr["out_b"], M)
+
+    # ------------------------------------------------------------------ encoder side
+    def _shape(self, x):
+        B, Cin, T, H, W = x.shape
+        if Cin != self.cin:
+            raise ValueError(f"expected {self.cin} channels, got {Cin}")
+        assert (T - 1) % self.pt == 0, (f"number of frames ({T}) minus one ({T - 1}) must be divisible by temporal "
+                                        f"patch size ({self.pt})")
+        if H != W or H % (self.p * self.ws) != 0:
+            raise ValueError(f"frames must be square with side a multiple of {self.p * self.ws} (got {H}x{W})")
+        return B, T, H, W, 1 + (T - 1) // self.pt, H // self.p, W // self.p
+
+    def encode_tokens(self, x: torch.Tensor):
+        """x (B,C,T,H,W) fp32 cuda -> (workspace with X = encoder output rows, dims).  omnitokenizer.py:881-947."""
+        x = x.contiguous()
+        B, T, H, W, Tp, h, w = self._shape(x)
+        N, M, C = h * w, B * Tp * h * w, self.C
+        ws = self._workspace(M)
+        pe = self.pe["first"]
+        k1 = self.cin * self.p * self.p
+        _cabi.call("omt_patchify_ln", x, ws.P, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p, self.pt, 1, 1e-5)
+        cmap = (N, Tp * N, 0)
+        self._linear(ws.P, k1, pe["lin"], ws.X, C, B * N, c_map=cmap)
+        self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], B * N, seg=cmap)
+        if Tp > 1:
+            pe = self.pe["rest"]
+            k2 = k1 * self.pt
+            rows = B * (Tp - 1) * N
+            _cabi.call("omt_patchify_ln", x, ws.P, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p, self.pt, 0,
+                       1e-5)
+            cmap = ((Tp - 1) * N, Tp * N, N)
+            self._linear(ws.P, k2, pe["lin"], ws.X, C, rows, c_map=cmap)
+            self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], rows, seg=cmap)
+        self._transformer(self.enc_spatial, ws, B, Tp, h, w, temporal=False)
+        self._transformer(self.enc_temporal, ws, B, Tp, h, w, temporal=True)
+        return ws, (B, Tp, h, w)
+
+    def pre_vq(self, ws: Workspace, l2: bool) -> torch.Tensor:
+        cd = self.pre_w.shape[0]
+        z = ws.z.view(-1)[: ws.M * cd].view(ws.M, cd)
+        _cabi.call("omt_pre_vq", ws.X, self.C, self.pre_w, self.pre_b, z, ws.M, self.C, cd, int(l2))
+        return z
+
+    def vq(self, ws: Workspace, z: torch.Tensor):
+        """modules/codebook.py:82-86 -> (idx int64 [M], counts int32 [n_codes])."""
+        ws.counts.zero_()
+        _cabi.call("omt_vq_search", z, self.E, self.e2, ws.M, self.n_codes, ws.idx, ws.counts, ws.vqws)
+        return ws.idx, ws.counts
+
+    # ------------------------------------------------------------------ decoder side
+    def decode_tokens(self, dims, *, idx=None, zc=None, z_st_from=None, zq_out=None, out=None):
+        """post_vq (+gather) -> temporal -> spatial -> to_pixels.  omnitokenizer.py:268-317, 1059-1118."""
+        B, Tp, h, w = dims
+        N, M, C = h * w, B * Tp * h * w, self.C
+        ws = self._workspace(M)
+        _cabi.call("omt_post_vq", idx, self.E if idx is not None else None, zc, z_st_from, zq_out, self.post_w,
+                   self.post_b, ws.X, M, C, self.post_w.shape[1])
+        self._transformer(self.dec_temporal, ws, B, Tp, h, w, temporal=True)
+        self._transformer(self.dec_spatial, ws, B, Tp, h, w, temporal=False)
+        T = 1 + (Tp - 1) * self.pt
+        H, W = h * self.p, w * self.p
+        video = out if out is not None else torch.empty(B, self.cin, T, H, W, device=self.device, dtype=torch.float32)
+        k1 = self.cin * self.p * self.p
+        self._linear(ws.X, C, self.px["first"], ws.P, k1, B * N, a_map=(N, Tp * N, 0))
+        _cabi.call("omt_unpatchify", ws.P, video, B, self.cin, T, H, W, self.p, self.pt, 1)
+        if Tp > 1:
+            k2 = k1 * self.pt
+            self._linear(ws.X, C, self.px["rest"], ws.P, k2, B * (Tp - 1) * N, a_map=((Tp - 1) * N, Tp * N, N))
+            _cabi.call("omt_unpatchify", ws.P, video, B, self.cin, T, H, W, self.p, self.pt, 0)
+        return video

@@ -1,0 +1,93 @@
+"""CPU tests: the oracle restatement vs the committed golden vectors (made by the UNMODIFIED reference,
+oracle/make_golden.py) and, when /root/reference is present, vs the reference itself."""
+import pytest
+import torch
+
+from oracle import omni_oracle as oo
+from oracle import ref_loader as rl
+from oracle import weights as W
+from tests.util import GOLDEN_CASES, check_sub, golden_setup, load_golden
+
+FAST = ["img64", "vid5x64", "vae_vid5x64", "vae_img64"]
+
+
+@pytest.mark.parametrize("name", FAST + ["vid9x128_b2", "img256_cfg1"])
+def test_oracle_matches_golden(name):
+    fx = load_golden(name)
+    cfg, sd, x = golden_setup(fx)
+    is_image = x.ndim == 4
+    with torch.no_grad():
+        if not cfg.use_vae:
+            emb, idx = oo.encode(sd, cfg, x, include_embeddings=True)
+            assert torch.equal(idx, fx["idx"].long()), "code indices differ from the reference"
+            check_sub(fx["emb"], emb, 1e-6, "embeddings")
+            rec = oo.decode(sd, cfg, idx, is_image)
+            check_sub(fx["rec"], rec, 2e-5, "reconstruction")
+            if is_image:
+                rec_flat = oo.decode(sd, cfg, idx.reshape(idx.shape[0], -1), True)
+                assert (rec_flat - rec).abs().max().item() <= fx["rec_flat_maxdiff"] + 1e-6
+        else:
+            z = oo.encode(sd, cfg, x, noise=fx["noise"])
+            check_sub(fx["z"], z, 2e-5, "vae latent")
+            rec = oo.decode(sd, cfg, z if is_image else z.permute(0, 2, 3, 4, 1), is_image)
+            check_sub(fx["rec"], rec, 5e-5, "vae reconstruction")
+
+
+@pytest.mark.parametrize("name", ["img64", "vid5x64"])
+def test_oracle_transformer_taps(name):
+    fx = load_golden(name)
+    cfg, sd, x = golden_setup(fx)
+    taps = {}
+    with torch.no_grad():
+        h, hw = oo.encoder(sd, cfg, x, taps)
+        B, T, N, C = taps["encoder_out"].shape
+        # reference temporal-transformer output is laid out (b h w) t d
+        ref_layout = taps["encoder_out"].permute(0, 2, 1, 3).reshape(B * N, T, C)
+        check_sub(fx["tap:encoder.enc_temporal_transformer"], ref_layout, 2e-5, "enc temporal out")
+
+
+def test_oracle_forward_log_image_stats():
+    fx = load_golden("img64")
+    cfg, sd, x = golden_setup(fx)
+    with torch.no_grad():
+        fr, frr, xx, xr, vq = oo.forward_log_image(sd, cfg, x)
+    check_sub(fx["fwd_rec"], xr, 2e-5, "forward recon")
+    assert torch.equal(vq["encodings"], fx["idx"].long())
+    for k in ("commitment_loss", "perplexity", "avg_usage"):
+        assert abs(float(vq[k]) - float(fx["fwd"][k])) <= 1e-5 * max(1.0, abs(float(fx["fwd"][k]))), k
+    assert int((vq["batch_usage"] > 0).sum()) == fx["fwd"]["batch_usage_nnz"]
+
+
+def test_peg_scrambled_map_is_a_permutation_free_gather():
+    rows, f = oo.peg_index_map(5, 8, 8, temporal=True, causal=True)
+    assert rows.shape == (5 * 64, 27)
+    assert int(rows.max()) < 5 * 64 and int(rows.min()) == -1
+    # centre tap (kt=2 causal, kh=1, kw=1) is the identity
+    assert torch.equal(rows[:, 2 * 9 + 4], torch.arange(5 * 64))
+
+
+def test_frame_count_assert():
+    cfg = oo.Config()
+    sd = W.make_state_dict(cfg, 0)
+    with pytest.raises(AssertionError):
+        oo.encode(sd, cfg, torch.zeros(1, 3, 6, 64, 64))
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not rl.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64), (1, 3, 5, 64, 64)])
+def test_oracle_matches_live_reference(shape):
+    m, args = rl.make_model(perturb=False)
+    cfg = oo.Config.from_args(args)
+    sd = W.make_state_dict(cfg, 3)
+    m.load_state_dict(sd, strict=False)
+    x = W.synthetic_input(shape, 99)
+    is_image = x.ndim == 4
+    with torch.no_grad():
+        emb_r, idx_r = m.encode(x, is_image, include_embeddings=True)
+        rec_r = m.decode(idx_r, is_image)
+        emb_o, idx_o = oo.encode(sd, cfg, x, include_embeddings=True)
+        rec_o = oo.decode(sd, cfg, idx_o, is_image)
+    assert torch.equal(idx_r, idx_o)
+    assert (emb_r - emb_o).abs().max() < 1e-6
+    assert (rec_r - rec_o).abs().max() < 2e-5
