@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- video-frames/s of OmniTokenizer_VQGAN encode -> codes -> decode (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2]
+
+Workload (config.workload): cfg3 = batch of 8 synthetic videos 17x256x256 (the configuration the
+metric is quoted on, BASELINE.json configs[2]); under torchrun the batch is split over ranks
+(strong scaling), each rank encodes its shard, ONE all-gather of code indices, decode of the shard.
+A "step" is one pass of that path over the batch.  Prints ONE JSON line (rank 0).
+
+--impl reference: the CPU baseline arm -- the oracle port of the reference's PyTorch path
+(oracle/omni_oracle.py; the reference tree itself does not travel to the GPU box) on all host
+threads, each step a bounded sample (one 17x256x256 video) of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg3": dict(shape=(8, 3, 17, 256, 256), desc="batch=8 videos 17x256x256 (UCF-shaped synthetic), VQVAE"),
+    "cfg2": dict(shape=(64, 3, 256, 256), desc="batch=64 images 256x256, VQVAE"),
+}
+# algorithmic FLOPs per batch: enc+dec, un-padded dims
+TFLOP = {"cfg3": 4.729, "cfg2": 7.500}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=5)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def make_model(dev):
+    import omnitokenizer_b200 as ob
+    torch.manual_seed(0)
+    m = ob.OmniTokenizer_VQGAN(ob.canonical_args())
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():      # move scales / LN gains off their ones init
+        for n, p in m.named_parameters():
+            if n.endswith(("q_scale", "k_scale", "gamma")) or (p.ndim == 1 and n.endswith(".weight")):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+    m.codebook._need_init = False
+    return m.to(dev).eval()
+
+
+def cpu_oracle_run(sd, x, reps=1):
+    from oracle import omni_oracle as oo
+    oo.USE_LIBRARY_OPS = True      # same torch library calls as the reference (conv3d PEG, SDPA)
+    cfg = oo.Config()
+    is_image = x.ndim == 4
+    best = None
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            idx = oo.encode(sd, cfg, x)
+            rec = oo.decode(sd, cfg, idx, is_image)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best, idx, rec
+
+
+def run_reference(args):
+    """CPU arm: oracle port of the reference path on the host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import omnitokenizer_b200 as ob
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = ob.OmniTokenizer_VQGAN(ob.canonical_args())
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    shape = (1,) + wl["shape"][1:]
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(1234)) - 0.5
+    frames = shape[2] if len(shape) == 5 else 1
+    for _ in range(args.warmup):
+        cpu_oracle_run(sd, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_run(sd, x)
+    dt = time.perf_counter() - t0
+    v = frames * args.steps / dt
+    sample = f"1 of {wl['shape'][0]} samples of the batch per step ({'x'.join(map(str, shape))})"
+    print(json.dumps({
+        "impl": "reference", "metric": "video_frames_per_sec_encode_decode", "value": round(v, 3), "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "sample": sample},
+        "cpu_baseline": {"value": round(v, 3), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def time_dominant_kernel(m, M, dev, flush):
+    """CUDA-event timing of the dominant kernel (FeedForward first Linear + GEGLU, 16 launches per
+    enc+dec) alone, same shapes as in the step: achieved algorithmic TFLOP/s."""
+    from omnitokenizer_b200 import _cabi
+    eng = m.engine()
+    lyr = eng.enc_spatial["layers"][0]
+    ws = eng._workspace(M)
+    ws.XN.normal_()
+    reps = 10
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i in range(reps + 2):
+        flush.add_(1.0)
+        if i >= 2:
+            evs[i - 2][0].record()
+        eng._linear(ws.XN, eng.C, lyr["ff1"], ws.U, eng.ku, M, epi=_cabi.EPI_GEGLU)
+        if i >= 2:
+            evs[i - 2][1].record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)[reps // 2]
+    flops = 2.0 * M * (2 * eng.inner) * eng.C          # un-padded algorithmic FLOPs of Linear(512 -> 2730)
+    return ms, flops
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--math", default=None, help="fp32 | 3xtf32 | tf32 (default: OMT_MATH or 3xtf32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.math:
+        os.environ["OMT_MATH"] = args.math
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import omnitokenizer_b200 as ob
+    from omnitokenizer_b200 import _cabi, dist as od
+    from omnitokenizer_b200.engine import default_math
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    shape = wl["shape"]
+    B = shape[0]
+    is_image = len(shape) == 4
+    frames_per_sample = 1 if is_image else shape[2]
+    s, e = od.shard_bounds(B, rank, world)
+    x_full = torch.rand(shape, generator=torch.Generator().manual_seed(1234)) - 0.5
+    x_host = x_full[s:e].contiguous().pin_memory()
+    x_dev = x_host.to(dev)
+    m = make_model(dev)
+    m.prepare()
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)      # 256 MiB > 126 MB L2
+
+    def step(x):
+        if x.shape[0] == 0:
+            codes = torch.empty((0,), dtype=torch.int64, device=dev)
+        else:
+            codes = m.encode(x, is_image)
+        if world > 1:
+            all_codes = od.all_gather_codes(codes, B)       # the single collective
+        if x.shape[0] == 0:
+            return None
+        return m.decode(codes, is_image)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    barrier()
+    # ---- device-timed region: K steps, L2 flushed (untimed) between steps ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _cabi.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        flush.add_(1.0)
+        a.record()
+        step(x_dev)
+        b.record()
+    barrier()
+    launches = _cabi.launch_count - n0
+    t_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- e2e: pinned host input -> H2D -> encode -> decode -> D2H of the reconstruction ----
+    out_host = torch.empty((e - s,) + shape[1:], dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, args.steps // 2)
+    evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+    barrier()
+    for a, b in evs2:
+        flush.add_(1.0)
+        a.record()
+        xd = x_host.to(dev, non_blocking=True)
+        rec = step(xd)
+        if rec is not None:
+            out_host.copy_(rec, non_blocking=True)
+        b.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t2_ms = sum(a.elapsed_time(b) for a, b in evs2)
+    tt = torch.tensor([t_ms, t2_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms, t2_ms = tt.tolist()
+    frames = B * frames_per_sample
+    value = frames * args.steps / (t_ms / 1e3)
+    e2e = frames * e2e_steps / (t2_ms / 1e3)
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        h, w = shape[-2] // 8, shape[-1] // 8
+        Tp = 1 if is_image else 1 + (shape[2] - 1) // 4
+        M_local = (e - s) * Tp * h * w
+        k_ms, k_flops = time_dominant_kernel(m, M_local, dev, flush)
+        math = default_math()
+        tf32_peak = pk["bf16_tflops"] / 2.0
+        achieved = k_flops / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": f"gemm_tc_kernel[{math}] FF1+GEGLU M={M_local} N=2730 K=512" if math != "fp32"
+                else f"gemm_fp32_kernel FF1+GEGLU M={M_local} N=2730 K=512",
+                "achieved": round(achieved, 2), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                "frac": round(achieved / tf32_peak, 4), "traffic": None, "ms_per_launch": round(k_ms, 4),
+                "peak_note": f"tf32 dense = 0.5 x {pk_src} bf16 burst {pk['bf16_tflops']} TF/s; FLOPs are algorithmic fp32 "
+                             f"(2MNK); 3xTF32 issues 3 MMAs per product so its own ceiling is 1/3 of this",
+                "whole_path": {"tflop_per_batch": TFLOP[args.workload],
+                               "achieved_tflops": round(TFLOP[args.workload] * args.steps / (t_ms / 1e3), 2)}}
+        line = {
+            "metric": "video_frames_per_sec_encode_decode", "value": round(value, 2), "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "global_batch": B, "frames": frames,
+                       "parallelism": f"batch-shard dp{world}, 1 all-gather of code indices", "math": math,
+                       "l2": "256 MiB flush between timed steps (untimed); activations >> L2"},
+            "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(t2_ms / e2e_steps, 3)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+            xs = x_full[:1]
+            cpu_oracle_run(sd, xs)                              # warm-up
+            dt, idx_o, rec_o = cpu_oracle_run(sd, xs, reps=2)
+            idx_g = m.encode(xs.to(dev), is_image)
+            rec_g = m.decode(idx_g, is_image)
+            line["cpu_baseline"] = {"value": round(frames_per_sample / dt, 3), "unit": "frames/s", "cores": cores,
+                                    "kind": "port",
+                                    "sample": f"1 of {B} samples ({'x'.join(map(str, xs.shape))}), best of 2 after warm-up"}
+            line["parity"] = {"idx_mismatch": int((idx_g.cpu() != idx_o).sum()), "n_idx": idx_o.numel(),
+                              "max_abs_pixel_err": float((rec_g.cpu() - rec_o).abs().max())}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,9 +82,16 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per entry point (for bench.py's gpu_launches accounting)
+KERNELS_PER_CALL = {"omt_vq_search": 2}
+launch_count = 0
+
+
 def call(name: str, *args):
     """Invoke an entry point on torch's current CUDA stream; tensors are converted to pointers."""
+    global launch_count
     lib = load()
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     conv = [_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a for a in args]
     rc = getattr(lib, name)(*conv, _stream())
     if rc != 0:

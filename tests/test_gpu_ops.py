@@ -1,0 +1,277 @@
+"""GPU op-level parity: every C-ABI kernel vs the oracle's restatement of the same reference op.
+Tolerances are fp32 round-off (different summation order), written next to each check."""
+import os
+
+import pytest
+import torch
+
+from oracle import omni_oracle as oo
+from oracle import weights as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _cabi():
+    from omnitokenizer_b200 import _cabi
+    _cabi.load()
+    return _cabi
+
+
+def _rand(shape, seed, scale=1.0):
+    return (torch.rand(shape, generator=torch.Generator().manual_seed(seed)) - 0.5) * 2 * scale
+
+
+def _pad128(w):
+    from omnitokenizer_b200 import layout as L
+    return L.pad_rows(w, 128)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 512, 512), (320, 192, 512), (1024, 1024, 768), (200, 512, 192)])
+@pytest.mark.parametrize("math", ["fp32", "3xtf32", "tf32"])
+def test_linear_plain_bias_residual(cuda, M, N, K, math):
+    cabi = _cabi()
+    from omnitokenizer_b200 import layout as L
+    if math != "fp32" and (K % 32 or M % 64):
+        pytest.skip("tcgen05 path needs K % 32 == 0 and 64-row granularity")
+    A, Wt, b, R = _rand((M, K), 1), _rand((N, K), 2, 0.05), _rand((N,), 3), _rand((M, N), 4)
+    ref = (A.double() @ Wt.double().t() + b.double() + R.double()).float()
+    Ad, bd, Rd = A.to(cuda), b.to(cuda), R.to(cuda)
+    Wp = _pad128(Wt).to(cuda)
+    mode = {"fp32": cabi.MATH_FP32, "3xtf32": cabi.MATH_3XTF32, "tf32": cabi.MATH_TF32}[math]
+    Wlo = None
+    if math == "3xtf32":
+        hi = L.tf32_round(Wp)
+        Wlo, Wp = (Wp - hi).contiguous(), hi
+    out = torch.full((M, N), float("nan"), device=cuda)
+    cabi.call("omt_linear", Ad, K, 0, 0, 0, Wp, Wlo, out, N, 0, 0, 0, M, N, K, bd, Rd, N, cabi.EPI_NONE, mode)
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    tol = {"fp32": 2e-5, "3xtf32": 2e-5, "tf32": 2e-2}[math]     # |A.W| ~ 1; tf32 single pass is ~1e-3 relative
+    assert err < tol, f"{math} M{M} N{N} K{K}: max err {err:.3e}"
+
+
+@pytest.mark.parametrize("math", ["fp32", "3xtf32"])
+def test_linear_geglu_and_rowmaps(cuda, math):
+    cabi = _cabi()
+    from omnitokenizer_b200 import layout as L
+    M, K, inner = 256, 512, 1365
+    ku = L.round_up(inner, 32)
+    A, W1 = _rand((M, K), 5), _rand((2 * inner, K), 6, 0.05)
+    y = A.double() @ W1.double().t()
+    ref = (oo.gelu_erf(y[:, inner:]) * y[:, :inner]).float()
+    mode = cabi.MATH_FP32 if math == "fp32" else cabi.MATH_3XTF32
+    Wp = _pad128(L.pack_geglu(W1, inner, ku)).to(cuda)
+    Wlo = None
+    if math == "3xtf32":
+        hi = L.tf32_round(Wp)
+        Wlo, Wp = (Wp - hi).contiguous(), hi
+    U = torch.full((M, ku), float("nan"), device=cuda)
+    cabi.call("omt_linear", A.to(cuda), K, 0, 0, 0, Wp, Wlo, U, ku, 0, 0, 0, M, 2 * ku, K, None, None, 0,
+              cabi.EPI_GEGLU, mode)
+    torch.cuda.synchronize()
+    assert (U[:, :inner].cpu() - ref).abs().max().item() < 2e-5
+    assert torch.count_nonzero(U[:, inner:]).item() == 0          # zero padding columns are exact
+    # row maps: logical rows scatter into / gather from the canonical buffer (first-frame / rest-frames)
+    B, T, N, Kp = 2, 3, 64, 192
+    X = _rand((B * T * N, 512), 7).to(cuda)
+    Wt = _rand((Kp, 512), 8, 0.05)
+    Wq = _pad128(Wt).to(cuda)
+    Wql = None
+    if math == "3xtf32":
+        hi = L.tf32_round(Wq)
+        Wql, Wq = (Wq - hi).contiguous(), hi
+    rows = B * (T - 1) * N
+    P = torch.empty(rows, Kp, device=cuda)
+    cabi.call("omt_linear", X, 512, (T - 1) * N, T * N, N, Wq, Wql, P, Kp, 0, 0, 0, rows, Kp, 512, None, None, 0,
+              cabi.EPI_NONE, mode)
+    sel = X.view(B, T, N, 512)[:, 1:].reshape(rows, 512).cpu()
+    assert (P.cpu() - (sel.double() @ Wt.double().t()).float()).abs().max().item() < 2e-5
+    Xo = torch.zeros(B * T * N, 512, device=cuda)
+    Wb = _pad128(_rand((512, Kp), 9, 0.05)).to(cuda)
+    Wbl = None
+    Wb_ref = Wb[:512].cpu()
+    if math == "3xtf32":
+        hi = L.tf32_round(Wb)
+        Wbl, Wb = (Wb - hi).contiguous(), hi
+    cabi.call("omt_linear", P, Kp, 0, 0, 0, Wb, Wbl, Xo, 512, (T - 1) * N, T * N, N, rows, 512, Kp, None, None, 0,
+              cabi.EPI_NONE, mode)
+    want = torch.zeros(B, T, N, 512)
+    want[:, 1:] = (P.cpu().double() @ Wb_ref.double().t()).float().view(B, T - 1, N, 512)
+    assert (Xo.cpu().view(B, T, N, 512) - want).abs().max().item() < 2e-5
+
+
+def test_layernorm_and_patchify(cuda):
+    cabi = _cabi()
+    x = _rand((300, 512), 10, 3.0)
+    g, b = _rand((512,), 11) + 1.0, _rand((512,), 12)
+    y = torch.empty(300, 512, device=cuda)
+    cabi.call("omt_layernorm", x.to(cuda), 512, y, 512, g.to(cuda), b.to(cuda), 300, 512, 1e-5, 0, 0, 0)
+    assert (y.cpu() - oo.layer_norm(x, g, b)).abs().max().item() < 5e-6
+    for shape in [(2, 3, 5, 64, 64), (1, 3, 1, 64, 64)]:
+        v = _rand(shape, 13, 0.5)
+        first, rest = oo.patchify(v, 8, 4)
+        for is_first, ref in ((1, first), (0, rest)):
+            if ref is None:
+                continue
+            K = ref.shape[-1]
+            lw, lb = _rand((K,), 14) + 1.0, _rand((K,), 15)
+            A = torch.empty(ref.numel() // K, K, device=cuda)
+            cabi.call("omt_patchify_ln", v.to(cuda), A, lw.to(cuda), lb.to(cuda), shape[0], 3, shape[2], 64, 64, 8, 4,
+                      is_first, 1e-5)
+            want = oo.layer_norm(ref, lw, lb).reshape(-1, K)
+            assert (A.cpu() - want).abs().max().item() < 5e-6
+            # un-patchify is the exact inverse permutation
+            vid = torch.zeros(shape, device=cuda)
+            raw = ref.reshape(-1, K).contiguous().to(cuda)
+            cabi.call("omt_unpatchify", raw, vid, shape[0], 3, shape[2], 64, 64, 8, 4, is_first)
+            got = vid.cpu()
+            want_v = v[:, :, :1] if is_first else v[:, :, 1:]
+            got_v = got[:, :, :1] if is_first else got[:, :, 1:]
+            assert torch.equal(got_v, want_v)
+
+
+@pytest.mark.parametrize("temporal", [False, True])
+@pytest.mark.parametrize("T", [1, 5])
+def test_peg(cuda, temporal, T):
+    cabi = _cabi()
+    from omnitokenizer_b200 import layout as L
+    B, h, w, C = 2, 8, 8, 512
+    X = _rand((B, T, h * w, C), 20)
+    wt, bias = _rand((C, 1, 3, 3, 3), 21, 0.3), _rand((C,), 22, 0.1)
+    want = oo.peg(X, wt, bias, (h, w), temporal, True) + X
+    nbr = L.peg_neighbour_table(T, h, w, temporal, True)
+    rows, _ = oo.peg_index_map(T, h, w, temporal, True)
+    assert torch.equal(nbr.long(), rows)
+    y = torch.empty(B * T * h * w, C, device=cuda)
+    cabi.call("omt_peg", X.reshape(-1, C).to(cuda), y, wt.reshape(C, 27).t().contiguous().to(cuda), bias.to(cuda),
+              nbr.to(cuda), B, T * h * w, C)
+    assert (y.cpu().view_as(want) - want).abs().max().item() < 1e-5
+
+
+def _attn_inputs(M, seed):
+    q, k, v = _rand((M, 512), seed), _rand((M, 512), seed + 1), _rand((M, 512), seed + 2)
+    qkv = torch.cat([q, k, v], dim=1).contiguous()
+    return q, k, v, qkv
+
+
+def test_qk_prep_and_spatial_attention(cuda):
+    cabi = _cabi()
+    from omnitokenizer_b200 import layout as L
+    nseq, N = 3, 256
+    M = nseq * N
+    q, k, v, qkv = _attn_inputs(M, 30)
+    qs, ks = _rand((64,), 33, 0.5) + 1.0, _rand((64,), 34, 0.5) + 1.0
+    cos, sin = L.rope_tables(N, 64)
+    c2, s2 = oo.rope_table(N, 64)
+    assert torch.equal(cos, c2) and torch.equal(sin, s2)
+    d = qkv.to(cuda)
+    p = d.data_ptr()
+    cabi.call("omt_qk_prep", p, 1536, p + 2048, 1536, qs.to(cuda), ks.to(cuda), cos.to(cuda), sin.to(cuda), M, N, 8)
+    q4 = oo.l2norm(oo.apply_rope(q.view(nseq, N, 8, 64), cos, sin)) * qs
+    k4 = oo.l2norm(oo.apply_rope(k.view(nseq, N, 8, 64), cos, sin)) * ks
+    got = d.cpu()
+    assert (got[:, :512].reshape(nseq, N, 8, 64) - q4).abs().max().item() < 2e-6
+    assert (got[:, 512:1024].reshape(nseq, N, 8, 64) - k4).abs().max().item() < 2e-6
+    assert torch.equal(got[:, 1024:], v)
+    o = torch.empty(M, 512, device=cuda)
+    cabi.call("omt_attn_spatial", p, 1536, p + 2048, 1536, p + 4096, 1536, o, 512, nseq, N, 8, 8.0)
+    qq, kk, vv = q4.permute(0, 2, 1, 3), k4.permute(0, 2, 1, 3), v.view(nseq, N, 8, 64).permute(0, 2, 1, 3)
+    want = torch.softmax((qq @ kk.transpose(-1, -2)) * 8.0, dim=-1) @ vv
+    want = want.permute(0, 2, 1, 3).reshape(M, 512)
+    assert (o.cpu() - want).abs().max().item() < 5e-6
+
+
+def test_window_attention(cuda):
+    cabi = _cabi()
+    from omnitokenizer_b200 import layout as L
+    cfg = oo.Config()
+    frames, h, w = 3, 16, 16
+    M = frames * h * w
+    q, k, v, qkv = _attn_inputs(M, 40)
+    table = _rand((225, 8), 43)
+    sd = W.make_state_dict(oo.Config(), 0)
+    index = sd["encoder.enc_spatial_transformer.layers.2.1.relative_position_index"]
+    bias = L.window_bias(table, index, 8)
+    d = qkv.to(cuda)
+    p = d.data_ptr()
+    o = torch.empty(M, 512, device=cuda)
+    cabi.call("omt_attn_window", p, 1536, p + 2048, 1536, p + 4096, 1536, o, 512, bias.to(cuda), frames, h, w, 8, 8,
+              0.125)
+    rows = oo.window_rows(h, w, 8)
+    def win(t):
+        return t.view(frames, h * w, 8, 64)[:, rows].permute(0, 1, 3, 2, 4)       # (f, nW, H, 64, D)
+    s = (win(q) * 0.125) @ win(k).transpose(-1, -2) + bias
+    ow = (torch.softmax(s, dim=-1) @ win(v)).permute(0, 1, 3, 2, 4).reshape(frames, rows.shape[0], 64, 512)
+    want = torch.empty(frames, h * w, 512)
+    want[:, rows] = ow
+    assert (o.cpu() - want.reshape(M, 512)).abs().max().item() < 5e-6
+
+
+@pytest.mark.parametrize("T,causal", [(1, 1), (5, 1), (9, 1), (5, 0)])
+def test_temporal_attention(cuda, T, causal):
+    cabi = _cabi()
+    B, N = 2, 64
+    M = B * T * N
+    q, k, v, qkv = _attn_inputs(M, 50)
+    d = qkv.to(cuda)
+    p = d.data_ptr()
+    o = torch.empty(M, 512, device=cuda)
+    cabi.call("omt_attn_temporal", p, 1536, p + 2048, 1536, p + 4096, 1536, o, 512, B, T, N, 8, 8.0, causal)
+    def seq(t):
+        return t.view(B, T, N, 8, 64).permute(0, 2, 3, 1, 4)                        # (B,N,H,T,D)
+    s = (seq(q) @ seq(k).transpose(-1, -2)) * 8.0
+    if causal:
+        s = s.masked_fill(torch.ones(T, T, dtype=torch.bool).triu(1), float("-inf"))
+    want = (torch.softmax(s, dim=-1) @ seq(v)).permute(0, 3, 1, 2, 4).reshape(M, 512)
+    assert (o.cpu() - want).abs().max().item() < 5e-6
+
+
+def test_vq_path(cuda):
+    cabi = _cabi()
+    M, C = 1000, 512
+    x = _rand((M, C), 60)
+    Wp, bp = _rand((8, C), 61, 0.05), _rand((8,), 62, 0.1)
+    E = torch.rand((8192, 8, 12), generator=torch.Generator().manual_seed(63)).sum(-1) - 6.0
+    z = torch.empty(M, 8, device=cuda)
+    cabi.call("omt_pre_vq", x.to(cuda), C, Wp.to(cuda), bp.to(cuda), z, M, C, 8, 1)
+    zr = x @ Wp.t() + bp
+    zr = zr / zr.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    assert (z.cpu() - zr).abs().max().item() < 2e-6
+    # search on the kernel's own z: must equal the oracle's argmin on the same z bit for bit
+    zc = z.cpu()
+    out = oo.codebook(E, zc)
+    e2 = (E.t() ** 2).sum(dim=0)
+    idx = torch.empty(M, dtype=torch.int64, device=cuda)
+    counts = torch.zeros(8192, dtype=torch.int32, device=cuda)
+    wsb = torch.empty(8 * M, device=cuda)
+    cabi.call("omt_vq_search", z, E.to(cuda), e2.to(cuda), M, 8192, idx, counts, wsb)
+    assert torch.equal(idx.cpu(), out["idx"])
+    assert torch.equal(counts.cpu().long(), torch.bincount(out["idx"], minlength=8192))
+    # ties: duplicated codes must resolve to the FIRST index (torch.argmin rule)
+    E2 = E.clone(); E2[4096:] = E[:4096]
+    e22 = (E2.t() ** 2).sum(dim=0)
+    counts.zero_()
+    cabi.call("omt_vq_search", z, E2.to(cuda), e22.to(cuda), M, 8192, idx, counts, wsb)
+    assert torch.equal(idx.cpu(), oo.codebook(E2, zc)["idx"]) and int(idx.max()) < 4096
+    # decode-side gather + post_vq, with and without straight-through rounding
+    Wq, bq = _rand((512, 8), 64, 0.3), _rand((512,), 65, 0.1)
+    X = torch.empty(M, 512, device=cuda)
+    idx_d = out["idx"].to(cuda)
+    cabi.call("omt_post_vq", idx_d, E.to(cuda), None, None, None, Wq.to(cuda), bq.to(cuda), X, M, 512, 8)
+    assert (X.cpu() - (E[out["idx"]] @ Wq.t() + bq)).abs().max().item() < 2e-6
+    zq = torch.empty(M, 8, device=cuda)
+    cabi.call("omt_post_vq", idx_d, E.to(cuda), None, z, zq, Wq.to(cuda), bq.to(cuda), X, M, 512, 8)
+    st = (E[out["idx"]] - zc) + zc
+    assert torch.equal(zq.cpu(), st)
+    assert (X.cpu() - (st @ Wq.t() + bq)).abs().max().item() < 2e-6
+    cabi.call("omt_post_vq", None, None, z, None, None, Wq.to(cuda), bq.to(cuda), X, M, 512, 8)
+    assert (X.cpu() - (zc @ Wq.t() + bq)).abs().max().item() < 2e-6
+
+
+def test_errors_are_loud(cuda):
+    cabi = _cabi()
+    x = torch.zeros(4, 512, device=cuda)
+    with pytest.raises(RuntimeError, match="omt_layernorm"):
+        cabi.call("omt_layernorm", x, 512, x, 512, x, None, 4, 514, 1e-5, 0, 0, 0)
+    with pytest.raises(RuntimeError, match="omt_attn_spatial"):
+        cabi.call("omt_attn_spatial", x, 512, x, 512, x, 512, x, 512, 1, 100, 8, 8.0)

@@ -91,3 +91,19 @@ def test_oracle_matches_live_reference(shape):
     assert torch.equal(idx_r, idx_o)
     assert (emb_r - emb_o).abs().max() < 1e-6
     assert (rec_r - rec_o).abs().max() < 2e-5
+
+
+def test_library_op_form_agrees_with_restatement():
+    """bench.py times the oracle with torch's fused library ops (the reference's own calls); both forms
+    must produce the same codes and pixels."""
+    fx = load_golden("vid5x64")
+    cfg, sd, x = golden_setup(fx)
+    try:
+        oo.USE_LIBRARY_OPS = True
+        with torch.no_grad():
+            idx = oo.encode(sd, cfg, x)
+            rec = oo.decode(sd, cfg, idx, False)
+    finally:
+        oo.USE_LIBRARY_OPS = False
+    assert torch.equal(idx, fx["idx"].long())
+    check_sub(fx["rec"], rec, 2e-5, "reconstruction (library-op form)")
