@@ -222,8 +222,9 @@ def test_temporal_attention(cuda, T, causal):
     s = (seq(q) @ seq(k).transpose(-1, -2)) * 8.0
     if causal:
         s = s.masked_fill(torch.ones(T, T, dtype=torch.bool).triu(1), float("-inf"))
-    want = (torch.softmax(s, dim=-1) @ seq(v)).permute(0, 3, 1, 2, 4).reshape(M, 512)
-    assert (o.cpu() - want).abs().max().item() < 5e-6
+    want = (torch.softmax(s.double(), dim=-1) @ seq(v).double()).permute(0, 3, 1, 2, 4).reshape(M, 512).float()
+    # un-normalised random q,k give |scale*q.k| ~ 50: exp() carries |s|*2^-24 ~ 3e-6 relative error per term
+    assert (o.cpu() - want).abs().max().item() < 2e-5
 
 
 def test_vq_path(cuda):
