@@ -91,6 +91,13 @@ int omt_unpatchify(const float* P, float* video, int B, int Cin, int T, int H, i
 int omt_peg(const float* x, float* y, const float* w27, const float* bias, const int32_t* nbr,
             int B, int rows_per_b, int C, omt_stream_t stream);
 
+/* Same operation as omt_peg, tiled: the stencil is evaluated in volume space (t2,h2,w2) with a
+ * shared-memory halo tile and a sliding register window (9 loads per output instead of 27).
+ * temporal != 0 selects the reference's literally-reshaped '(b h w) t d' volume (attention.py:313-319),
+ * causal != 0 pads t by (2,0) instead of (1,1).  x, y: canonical [B*T*h*w, C]. */
+int omt_peg_volume(const float* x, float* y, const float* w27, const float* bias, int B, int T, int h, int w,
+                   int C, int temporal, int causal, omt_stream_t stream);
+
 /* In-place rope + l2norm + per-dim scale on q and k (attention.py:417-421, :435-437).
  * q[M, heads*64] (ld ldq), k likewise; cos/sin [N, 32] or NULL (no rope; temporal blocks);
  * the rope position of row r is r % N. */

@@ -236,6 +236,87 @@ __global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, f
 }
 
 // ------------------------------------------------------------------------------------------
+// PEG, tiled form.  The stencil lives in "volume space" (t2,h2,w2): for spatial transformers that
+// is the true token grid; for temporal ones it is the reference's literal reshape of the
+// '(b h w) t d' tensor (flat f = n*T + tau unravelled over (T,h,w)).  Either way volume position f
+// maps to canonical row  temporal ? (f % T) * N + f / T : f.
+// One CTA stages a (TT+2) x (HB+2) x (w+2) x 16-channel halo tile in shared memory (zeros where the
+// reference pads), then every thread owns one (plane, row, channel-pair) strip and slides a
+// 3x3x3 register window along w: 9 shared loads per output instead of 27 global ones.
+// ------------------------------------------------------------------------------------------
+constexpr int PEG_CC = 16;       // channels per CTA
+
+__global__ void __launch_bounds__(256) peg_tile_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                       const float* __restrict__ w27,
+                                                       const float* __restrict__ bias, int T, int h, int w,
+                                                       int C, int temporal, int causal, int TT, int HB, int RS) {
+  extern __shared__ __align__(16) float tile[];      // [(TT+2)][(HB+2)] rows of RS floats ((w+2)*16 + pad)
+  const int N = h * w;
+  const int n_hblk = (h + HB - 1) / HB;
+  const int t0 = (blockIdx.x / n_hblk) * TT, h0 = (blockIdx.x % n_hblk) * HB;
+  const int c0 = blockIdx.y * PEG_CC;
+  const long long bbase = (long long)blockIdx.z * T * N;
+  const int pad_lo = causal ? 2 : 1;
+  const int rows = (TT + 2) * (HB + 2);
+  const int nth = blockDim.x;
+  // ---- stage the halo tile
+  const int total4 = rows * (w + 2) * (PEG_CC / 4);
+  for (int i = threadIdx.x; i < total4; i += nth) {
+    const int c4 = i & 3;
+    int pos = i >> 2;
+    const int pw = pos % (w + 2); pos /= (w + 2);
+    const int ph = pos % (HB + 2);
+    const int pt = pos / (HB + 2);
+    const int t2 = t0 - pad_lo + pt, h2 = h0 - 1 + ph, w2 = pw - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t2 >= 0 && t2 < T && h2 >= 0 && h2 < h && w2 >= 0 && w2 < w) {
+      const int f = (t2 * h + h2) * w + w2;
+      const int row = temporal ? (f % T) * N + f / T : f;
+      v = __ldg(reinterpret_cast<const float4*>(x + (bbase + row) * C + c0) + c4);
+    }
+    *reinterpret_cast<float4*>(tile + (pt * (HB + 2) + ph) * RS + pw * PEG_CC + c4 * 4) = v;
+  }
+  __syncthreads();
+  // ---- strips
+  const int cp = threadIdx.x & 7;                  // channel pair inside the 16-channel slab
+  const int strip = threadIdx.x >> 3;
+  const int sh = strip % HB, st = strip / HB;
+  if (st >= TT || t0 + st >= T || h0 + sh >= h) return;
+  float2 wt[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) wt[k] = *reinterpret_cast<const float2*>(w27 + (size_t)k * C + c0 + 2 * cp);
+  const float2 bb = *reinterpret_cast<const float2*>(bias + c0 + 2 * cp);
+  float2 win[9][3];
+  const float* tp = tile + 2 * cp;
+#pragma unroll
+  for (int r9 = 0; r9 < 9; ++r9) {
+    const float* rp = tp + ((st + r9 / 3) * (HB + 2) + sh + r9 % 3) * RS;
+    win[r9][1] = *reinterpret_cast<const float2*>(rp);
+    win[r9][2] = *reinterpret_cast<const float2*>(rp + PEG_CC);
+  }
+  const int fbase = ((t0 + st) * h + (h0 + sh)) * w;
+  for (int w2 = 0; w2 < w; ++w2) {
+    float2 acc = bb;
+#pragma unroll
+    for (int r9 = 0; r9 < 9; ++r9) {
+      const float* rp = tp + ((st + r9 / 3) * (HB + 2) + sh + r9 % 3) * RS + (w2 + 2) * PEG_CC;
+      win[r9][0] = win[r9][1]; win[r9][1] = win[r9][2];
+      win[r9][2] = *reinterpret_cast<const float2*>(rp);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        acc.x = fmaf(win[r9][kw].x, wt[r9 * 3 + kw].x, acc.x);
+        acc.y = fmaf(win[r9][kw].y, wt[r9 * 3 + kw].y, acc.y);
+      }
+    }
+    const float2 ctr = causal ? win[7][1] : win[4][1];   // the un-shifted token itself (residual)
+    acc.x += ctr.x; acc.y += ctr.y;
+    const int f = fbase + w2;
+    const int row = temporal ? (f % T) * N + f / T : f;
+    *reinterpret_cast<float2*>(y + (bbase + row) * C + c0 + 2 * cp) = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // rope + l2norm + scale, in place on q and k.  One warp per row; lane l owns the complex pair
 // (2l, 2l+1) of every head.
 // ------------------------------------------------------------------------------------------
@@ -389,6 +470,35 @@ extern "C" int omt_peg(const float* x, float* y, const float* w27, const float* 
   }
   const unsigned blocks = (unsigned)((M + PEG_ROWS - 1) / PEG_ROWS);
   peg_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(x, y, w27, bias, nbr, rows_per_b, C, M);
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
+extern "C" int omt_peg_volume(const float* x, float* y, const float* w27, const float* bias, int B, int T, int h,
+                              int w, int C, int temporal, int causal, omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(x && y && w27 && bias, "omt_peg_volume: null pointer");
+  OMT_REQUIRE(x != y, "omt_peg_volume: in-place is not supported (stencil)");
+  OMT_REQUIRE(C % PEG_CC == 0 && C / PEG_CC <= 65535 && B <= 65535, "omt_peg_volume: C=%d must be a multiple of 16", C);
+  OMT_REQUIRE(T >= 1 && h >= 1 && w >= 1, "omt_peg_volume: bad volume");
+  if (B == 0) return OMT_OK;
+  // tile geometry: planes per CTA (TT) and rows per CTA (HB) so that threads <= 256 and smem <= ~100 KB
+  int RS = (w + 2) * PEG_CC;
+  RS += ((16 - RS % 32) + 32) % 32;                  // row stride == 16 (mod 32) floats: 2-way minimum bank pattern
+  int TT = T < 5 ? T : 5, HB = 4;
+  auto smem_of = [&](int tt, int hb) { return (size_t)(tt + 2) * (hb + 2) * RS * sizeof(float); };
+  while (HB > 1 && (smem_of(TT, HB) > 100 * 1024 || TT * HB * 8 > 256)) --HB;
+  while (TT > 1 && (smem_of(TT, HB) > 100 * 1024 || TT * HB * 8 > 256)) --TT;
+  const size_t smem = smem_of(TT, HB);
+  OMT_REQUIRE(smem <= 200 * 1024, "omt_peg_volume: row of %d tokens does not fit the shared-memory tile", w);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    OMT_CUDA(cudaFuncSetAttribute(peg_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int threads = ((TT * HB * 8 + 31) / 32) * 32;
+  dim3 grid(((T + TT - 1) / TT) * ((h + HB - 1) / HB), C / PEG_CC, B);
+  peg_tile_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS);
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }

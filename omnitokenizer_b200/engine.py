@@ -54,8 +54,9 @@ class Workspace:
     def __init__(self, device, M: int, C: int, ku: int, kmax: int, cd: int):
         f = dict(device=device, dtype=torch.float32)
         self.M = M
-        self.X = torch.empty(M, C, **f)
-        self.Y = torch.empty(M, C, **f)
+        self.buf0 = torch.empty(M, C, **f)
+        self.buf1 = torch.empty(M, C, **f)
+        self.X, self.Y = self.buf0, self.buf1
         self.XN = torch.empty(M, C, **f)
         self.QKV = torch.empty(M, 3 * C, **f)
         self.O = torch.empty(M, C, **f)
@@ -65,6 +66,16 @@ class Workspace:
         self.idx = torch.empty(M, device=device, dtype=torch.int64)
         self.counts = torch.zeros(8192, device=device, dtype=torch.int32)
         self.vqws = torch.empty(4 * M * 2, **f)
+        # static I/O buffers + captured CUDA graphs of this shape
+        self.x_in = None
+        self.idx_in = torch.empty(M, device=device, dtype=torch.int64)
+        self.zc_in = torch.empty(M, cd, **f)
+        self.zq = torch.empty(M, cd, **f)
+        self.video = None
+        self.graphs = {}
+
+    def reset(self):
+        self.X, self.Y = self.buf0, self.buf1
 
 
 class Engine:
@@ -172,7 +183,8 @@ class Engine:
             ws = Workspace(self.device, M, self.C, self.ku, kmax, max(self.cd, 16))
             if ws.counts.numel() < self.n_codes:
                 ws.counts = torch.zeros(self.n_codes, device=self.device, dtype=torch.int32)
-            self._ws.clear()          # keep one shape resident
+            while len(self._ws) >= 3:  # keep a few shapes (and their graphs) resident
+                self._ws.pop(next(iter(self._ws)))
             self._ws[M] = ws
         return ws
 
@@ -201,9 +213,8 @@ class Engine:
         ld3 = 3 * C
         for lyr in tr["layers"]:
             if lyr["kind"] == "t":
-                nbr = self._table(("peg", T, h, w, temporal, self.causal_peg),
-                                  lambda: L.peg_neighbour_table(T, h, w, temporal, self.causal_peg))
-                _cabi.call("omt_peg", ws.X, ws.Y, lyr["peg_w"], lyr["peg_b"], nbr, B, T * N, C)
+                _cabi.call("omt_peg_volume", ws.X, ws.Y, lyr["peg_w"], lyr["peg_b"], B, T, h, w, C, int(temporal),
+                           int(self.causal_peg))
                 ws.X, ws.Y = ws.Y, ws.X
                 self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
                 self._linear(ws.XN, C, lyr["to_q"], q_ptr, ld3, M)            # q from the normalised input
@@ -231,9 +242,9 @@ class Engine:
             self._linear(ws.U, self.ku, lyr["ff2"], ws.X, C, M, residual=ws.X, ldr=C)
         self._ln(ws.X, ws.X, tr["out_g"], tr["out_b"], M)
 
-    # ------------------------------------------------------------------ encoder side
-    def _shape(self, x):
-        B, Cin, T, H, W = x.shape
+    # ------------------------------------------------------------------ shapes / graphs
+    def _shape(self, shape):
+        B, Cin, T, H, W = shape
         if Cin != self.cin:
             raise ValueError(f"expected {self.cin} channels, got {Cin}")
         assert (T - 1) % self.pt == 0, (f"number of frames ({T}) minus one ({T - 1}) must be divisible by temporal "
@@ -242,12 +253,38 @@ class Engine:
             raise ValueError(f"frames must be square with side a multiple of {self.p * self.ws} (got {H}x{W})")
         return B, T, H, W, 1 + (T - 1) // self.pt, H // self.p, W // self.p
 
-    def encode_tokens(self, x: torch.Tensor):
-        """x (B,C,T,H,W) fp32 cuda -> (workspace with X = encoder output rows, dims).  omnitokenizer.py:881-947."""
-        x = x.contiguous()
-        B, T, H, W, Tp, h, w = self._shape(x)
-        N, M, C = h * w, B * Tp * h * w, self.C
-        ws = self._workspace(M)
+    @staticmethod
+    def graphs_enabled() -> bool:
+        return os.environ.get("OMT_CUDA_GRAPH", "1") != "0"
+
+    def _run(self, ws: Workspace, key, body):
+        """Run ``body`` (a fixed launch sequence over static buffers): the first call of a shape runs eagerly
+        (sets function attributes, builds tables), the second captures a CUDA graph, later calls replay it --
+        ~170 launches per encode+decode collapse into one submission."""
+        if not self.graphs_enabled():
+            return body()
+        g = ws.graphs.get(key)
+        if g is None:
+            body()
+            ws.graphs[key] = "warm"
+        elif g == "warm":
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            n0 = _cabi.launch_count
+            with torch.cuda.graph(graph):
+                body()
+            ws.graphs[key] = (graph, _cabi.launch_count - n0)
+            graph.replay()
+        else:
+            g[0].replay()
+            _cabi.launch_count += g[1]        # kernels inside the replayed graph (bench.py accounting)
+
+    # ------------------------------------------------------------------ encoder side
+    def _encode_body(self, ws: Workspace, x, dims, mode: str):
+        """patch embed -> spatial -> temporal -> pre_vq [-> VQ search].  omnitokenizer.py:881-947, 247-258."""
+        B, T, H, W, Tp, h, w = dims
+        N, C = h * w, self.C
+        ws.reset()
         pe = self.pe["first"]
         k1 = self.cin * self.p * self.p
         _cabi.call("omt_patchify_ln", x, ws.P, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p, self.pt, 1, 1e-5)
@@ -265,38 +302,80 @@ class Engine:
             self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], rows, seg=cmap)
         self._transformer(self.enc_spatial, ws, B, Tp, h, w, temporal=False)
         self._transformer(self.enc_temporal, ws, B, Tp, h, w, temporal=True)
-        return ws, (B, Tp, h, w)
-
-    def pre_vq(self, ws: Workspace, l2: bool) -> torch.Tensor:
         cd = self.pre_w.shape[0]
         z = ws.z.view(-1)[: ws.M * cd].view(ws.M, cd)
-        _cabi.call("omt_pre_vq", ws.X, self.C, self.pre_w, self.pre_b, z, ws.M, self.C, cd, int(l2))
-        return z
+        _cabi.call("omt_pre_vq", ws.X, C, self.pre_w, self.pre_b, z, ws.M, C, cd, int(mode == "vq" and self.l2))
+        if mode == "vq":      # modules/codebook.py:82-86
+            ws.counts.zero_()
+            _cabi.call("omt_vq_search", z, self.E, self.e2, ws.M, self.n_codes, ws.idx, ws.counts, ws.vqws)
 
-    def vq(self, ws: Workspace, z: torch.Tensor):
-        """modules/codebook.py:82-86 -> (idx int64 [M], counts int32 [n_codes])."""
-        ws.counts.zero_()
-        _cabi.call("omt_vq_search", z, self.E, self.e2, ws.M, self.n_codes, ws.idx, ws.counts, ws.vqws)
-        return ws.idx, ws.counts
+    def encode(self, x: torch.Tensor, mode: str):
+        """x (B,C,T,H,W) fp32 on the device.  mode 'vq': returns (ws, dims) with ws.z (l2-normalised z),
+        ws.idx, ws.counts filled; mode 'raw': ws.z = pre_vq output (VAE moments).  Results live in the
+        workspace until the next call of the same shape."""
+        dims = self._shape(tuple(x.shape))
+        B, T, H, W, Tp, h, w = dims
+        ws = self._workspace(B * Tp * h * w)
+        if ws.x_in is None or ws.x_in.shape != x.shape:
+            ws.x_in = torch.empty_like(x, memory_format=torch.contiguous_format)
+            ws.graphs = {k: v for k, v in ws.graphs.items() if not k[0].startswith("enc")}
+        ws.x_in.copy_(x)
+        self._run(ws, ("enc:" + mode, tuple(x.shape)), lambda: self._encode_body(ws, ws.x_in, dims, mode))
+        return ws, (B, Tp, h, w)
+
+    def z_view(self, ws: Workspace) -> torch.Tensor:
+        return self._dense(ws.z, ws.M, self.pre_w.shape[0])
+
+    @staticmethod
+    def _dense(buf: torch.Tensor, M: int, cols: int) -> torch.Tensor:
+        """Dense [M, cols] view at the start of a wider scratch buffer (kernels take packed rows)."""
+        return buf.view(-1)[: M * cols].view(M, cols)
+
+    def zq_view(self, ws: Workspace) -> torch.Tensor:
+        return self._dense(ws.zq, ws.M, self.post_w.shape[1])
 
     # ------------------------------------------------------------------ decoder side
-    def decode_tokens(self, dims, *, idx=None, zc=None, z_st_from=None, zq_out=None, out=None):
-        """post_vq (+gather) -> temporal -> spatial -> to_pixels.  omnitokenizer.py:268-317, 1059-1118."""
+    def _decode_body(self, ws: Workspace, dims, mode: str):
+        """[gather +] post_vq -> temporal -> spatial -> to_pixels.  omnitokenizer.py:268-317, 1059-1118."""
         B, Tp, h, w = dims
-        N, M, C = h * w, B * Tp * h * w, self.C
-        ws = self._workspace(M)
-        _cabi.call("omt_post_vq", idx, self.E if idx is not None else None, zc, z_st_from, zq_out, self.post_w,
-                   self.post_b, ws.X, M, C, self.post_w.shape[1])
+        N, M, C = h * w, ws.M, self.C
+        ws.reset()
+        cdp = self.post_w.shape[1]
+        if mode == "idx":
+            _cabi.call("omt_post_vq", ws.idx_in, self.E, None, None, None, self.post_w, self.post_b, ws.X, M, C, cdp)
+        elif mode == "idx_st":    # forward(): decoder sees (E[idx] - z) + z, codebook.py:120
+            _cabi.call("omt_post_vq", ws.idx_in, self.E, None, self.z_view(ws), self.zq_view(ws), self.post_w,
+                       self.post_b, ws.X, M, C, cdp)
+        else:
+            _cabi.call("omt_post_vq", None, None, self._dense(ws.zc_in, M, cdp), None, None, self.post_w, self.post_b,
+                       ws.X, M, C, cdp)
         self._transformer(self.dec_temporal, ws, B, Tp, h, w, temporal=True)
         self._transformer(self.dec_spatial, ws, B, Tp, h, w, temporal=False)
         T = 1 + (Tp - 1) * self.pt
         H, W = h * self.p, w * self.p
-        video = out if out is not None else torch.empty(B, self.cin, T, H, W, device=self.device, dtype=torch.float32)
         k1 = self.cin * self.p * self.p
         self._linear(ws.X, C, self.px["first"], ws.P, k1, B * N, a_map=(N, Tp * N, 0))
-        _cabi.call("omt_unpatchify", ws.P, video, B, self.cin, T, H, W, self.p, self.pt, 1)
+        _cabi.call("omt_unpatchify", ws.P, ws.video, B, self.cin, T, H, W, self.p, self.pt, 1)
         if Tp > 1:
             k2 = k1 * self.pt
             self._linear(ws.X, C, self.px["rest"], ws.P, k2, B * (Tp - 1) * N, a_map=((Tp - 1) * N, Tp * N, N))
-            _cabi.call("omt_unpatchify", ws.P, video, B, self.cin, T, H, W, self.p, self.pt, 0)
-        return video
+            _cabi.call("omt_unpatchify", ws.P, ws.video, B, self.cin, T, H, W, self.p, self.pt, 0)
+
+    def decode(self, dims, *, idx=None, zc=None, straight_through=False) -> torch.Tensor:
+        """dims (B,T',h,w).  idx: int64 [M] codes | zc: fp32 [M, cd] latents (VAE).  With straight_through
+        the rows are (E[idx] - z) + z using the z left in the workspace by encode(); ws.zq receives them.
+        Returns a fresh (B,C,T,H,W) tensor (the reference's decoder ends in .clone(), omnitokenizer.py:1116)."""
+        B, Tp, h, w = dims
+        ws = self._workspace(B * Tp * h * w)
+        vshape = (B, self.cin, 1 + (Tp - 1) * self.pt, h * self.p, w * self.p)
+        if ws.video is None or tuple(ws.video.shape) != vshape:
+            ws.video = torch.empty(vshape, device=self.device, dtype=torch.float32)
+            ws.graphs = {k: v for k, v in ws.graphs.items() if not k[0].startswith("dec")}
+        if idx is not None:
+            ws.idx_in.copy_(idx.reshape(-1))
+            mode = "idx_st" if straight_through else "idx"
+        else:
+            self._dense(ws.zc_in, ws.M, zc.shape[1]).copy_(zc)
+            mode = "zc"
+        self._run(ws, ("dec:" + mode, dims), lambda: self._decode_body(ws, dims, mode))
+        return ws.video.clone()

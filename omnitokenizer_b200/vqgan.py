@@ -283,17 +283,16 @@ class OmniTokenizer_VQGAN(nn.Module):
         eng = self.engine()
         with torch.cuda.device(self.device):
             xv = x.unsqueeze(2) if is_image else x
-            ws, (B, Tp, h, w) = eng.encode_tokens(xv.float())
+            ws, (B, Tp, h, w) = eng.encode(xv.float(), "raw" if self.use_vae else "vq")
             if not self.use_vae:
-                z = eng.pre_vq(ws, l2=self.l2_code)
-                idx, _ = eng.vq(ws, z)
-                enc = idx.view(B, Tp, h, w).clone()
+                enc = ws.idx.view(B, Tp, h, w).clone()
                 if include_embeddings:
-                    e = eng.E[idx]
+                    z = eng.z_view(ws)
+                    e = eng.E[ws.idx]
                     st = (e - z) + z
                     return st.view(B, Tp, h, w, -1).permute(0, 4, 1, 2, 3).contiguous(), enc
                 return enc
-            hpar = eng.pre_vq(ws, l2=False)                                       # (M, 2*cd)
+            hpar = eng.z_view(ws)                                                 # (M, 2*cd) moments
             c = hpar.shape[1] // 2
             hpar = hpar.view(B, Tp, h, w, 2 * c).permute(0, 4, 1, 2, 3)
             mean, logvar = hpar[:, :c], torch.clamp(hpar[:, c:], -30.0, 20.0)     # vae.py:7-8
@@ -318,8 +317,8 @@ class OmniTokenizer_VQGAN(nn.Module):
                     raise ValueError("image indices must be (B, h*w) or (B, 1, h, w)")
                 else:
                     B, Tp, h, w = enc.shape
-                idx = enc.reshape(-1).to(device=self.device, dtype=torch.int64).contiguous()
-                video = eng.decode_tokens((B, Tp, h, w), idx=idx)
+                idx = enc.reshape(-1).to(device=self.device, dtype=torch.int64)
+                video = eng.decode((B, Tp, h, w), idx=idx)
             else:
                 z = encodings.to(device=self.device, dtype=torch.float32)
                 if is_image:
@@ -336,7 +335,7 @@ class OmniTokenizer_VQGAN(nn.Module):
                     else:
                         B, Tp, h, w, c = z.shape
                         zc = z.reshape(B * Tp * h * w, c)
-                video = eng.decode_tokens((B, Tp, h, w), zc=zc.contiguous())
+                video = eng.decode((B, Tp, h, w), zc=zc)
             return video.squeeze(2) if is_image else video
 
     @torch.no_grad()
@@ -350,16 +349,15 @@ class OmniTokenizer_VQGAN(nn.Module):
         is_image = x.ndim == 4
         with torch.cuda.device(self.device):
             xv = (x.unsqueeze(2) if is_image else x).float()
-            ws, dims = eng.encode_tokens(xv)
+            ws, dims = eng.encode(xv, "raw" if self.use_vae else "vq")
             B, Tp, h, w = dims
             M = ws.M
             vq_output = None
             if not self.use_vae:
-                z = eng.pre_vq(ws, l2=self.l2_code).clone()
-                idx, counts = eng.vq(ws, z)
-                idx = idx.clone()
-                zq = torch.empty_like(z)
-                x_recon = eng.decode_tokens(dims, idx=idx, z_st_from=z, zq_out=zq)   # decoder sees (e - z) + z
+                z = eng.z_view(ws).clone()
+                idx, counts = ws.idx.clone(), ws.counts.clone()
+                x_recon = eng.decode(dims, idx=idx, straight_through=True)           # decoder sees (e - z) + z
+                zq = eng.zq_view(ws).clone()
                 cb = self.codebook
                 n_codes = cb.n_codes
                 usage = counts[:n_codes].float() / M                                  # codebook.py:54-72 (fixed-size histogram)
@@ -376,14 +374,14 @@ class OmniTokenizer_VQGAN(nn.Module):
                                  encodings=idx.view(B, Tp, h, w), commitment_loss=commitment, perplexity=perplexity,
                                  avg_usage=avg_usage, batch_usage=usage)
             else:
-                hpar = eng.pre_vq(ws, l2=False)
+                hpar = eng.z_view(ws)
                 c = hpar.shape[1] // 2
                 hp5 = hpar.view(B, Tp, h, w, 2 * c).permute(0, 4, 1, 2, 3)
                 mean, logvar = hp5[:, :c], torch.clamp(hp5[:, c:], -30.0, 20.0)
                 noise = torch.randn(mean.shape).to(device=self.device)               # drawn BEFORE randint (:368 vs :401)
                 z = mean + torch.exp(0.5 * logvar) * noise
                 zc = z.permute(0, 2, 3, 4, 1).reshape(M, c).contiguous()
-                x_recon = eng.decode_tokens(dims, zc=zc)
+                x_recon = eng.decode(dims, zc=zc)
             if is_image:
                 x_recon = x_recon.squeeze(2)
                 frames, frames_recon = x, x_recon

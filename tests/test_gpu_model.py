@@ -66,7 +66,7 @@ def test_intermediate_activations_vs_oracle(cuda, math):
     taps = {}
     with torch.no_grad():
         oo.encoder(sd, cfg, x, taps)
-    ws, dims = eng.encode_tokens(x.to(cuda))
+    ws, dims = eng.encode(x.to(cuda), "vq")
     got = ws.X.cpu().view(taps["encoder_out"].shape)
     err = (got - taps["encoder_out"]).abs().max().item()
     assert err < 2e-4, f"encoder output differs from oracle by {err:.2e}"

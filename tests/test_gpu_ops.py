@@ -146,6 +146,24 @@ def test_peg(cuda, temporal, T):
     cabi.call("omt_peg", X.reshape(-1, C).to(cuda), y, wt.reshape(C, 27).t().contiguous().to(cuda), bias.to(cuda),
               nbr.to(cuda), B, T * h * w, C)
     assert (y.cpu().view_as(want) - want).abs().max().item() < 1e-5
+    y2 = torch.empty_like(y)
+    cabi.call("omt_peg_volume", X.reshape(-1, C).to(cuda), y2, wt.reshape(C, 27).t().contiguous().to(cuda),
+              bias.to(cuda), B, T, h, w, C, int(temporal), 1)
+    assert (y2.cpu().view_as(want) - want).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("T,h,w,temporal,causal", [(9, 16, 16, True, True), (3, 8, 16, False, False),
+                                                   (2, 8, 8, True, False), (5, 64, 64, True, True)])
+def test_peg_volume_shapes(cuda, T, h, w, temporal, causal):
+    cabi = _cabi()
+    B, C = 1, 64
+    X = _rand((B, T, h * w, C), 23)
+    wt, bias = _rand((C, 1, 3, 3, 3), 24, 0.3), _rand((C,), 25, 0.1)
+    want = oo.peg(X, wt, bias, (h, w), temporal, causal) + X
+    y = torch.empty(B * T * h * w, C, device=cuda)
+    cabi.call("omt_peg_volume", X.reshape(-1, C).to(cuda), y, wt.reshape(C, 27).t().contiguous().to(cuda),
+              bias.to(cuda), B, T, h, w, C, int(temporal), int(causal))
+    assert (y.cpu().view_as(want) - want).abs().max().item() < 1e-5
 
 
 def _attn_inputs(M, seed):
