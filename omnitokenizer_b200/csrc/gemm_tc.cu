@@ -339,7 +339,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensor
 
 }  // namespace tc
 
-static int g_tc_bn = 128;   // tile-N selector (set through omt_set_option for tuning)
+static int g_tc_bn = 128;   // tile-N selector of the v1 kernel (set through omt_set_option for tuning)
+static int g_tc_kernel = 2; // 2 = persistent 2-CTA kernel (gemm_tc2.cu) for 3xTF32, 1 = one-tile-per-CTA kernel
+
+int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st);
 
 int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math, cudaStream_t st) {
   using namespace tc;
@@ -349,6 +352,7 @@ int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math,
     OMT_REQUIRE(g.a_seg % 64 == 0 && g.M % g.a_seg == 0, "omt_linear(tcgen05): A row-map segment %d must be a multiple of 64 dividing M=%d", g.a_seg, g.M);
   }
   const bool split = (math == OMT_MATH_3XTF32);
+  if (split && g_tc_kernel == 2) return launch_gemm_tc2(g, W_lo, epilogue, st);
   const int n_pad = (g.N + 127) / 128 * 128;
   CUtensorMap tmA, tmW, tmWlo;
   {
@@ -385,6 +389,11 @@ extern "C" int omt_set_option(const char* name, int value) {
   if (strcmp(name, "tc_block_n") == 0) {
     if (value != 128 && value != 256) { omt::set_error("tc_block_n must be 128 or 256"); return OMT_E_ARG; }
     omt::g_tc_bn = value;
+    return OMT_OK;
+  }
+  if (strcmp(name, "tc_kernel") == 0) {
+    if (value != 1 && value != 2) { omt::set_error("tc_kernel must be 1 or 2"); return OMT_E_ARG; }
+    omt::g_tc_kernel = value;
     return OMT_OK;
   }
   omt::set_error("unknown option %s", name);

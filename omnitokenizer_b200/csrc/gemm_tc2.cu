@@ -1,0 +1,399 @@
+// GEMM v2: persistent, 2-CTA (cta_group::2) tcgen05 GEMM with 3xTF32 error compensation.
+//
+//   C[M,N] = A[M,K] . W[N,K]^T (+bias)(+residual) | GEGLU,   fp32 in / out, fp32-grade accuracy.
+//
+// Why 2 CTAs: tf32 operands are 4 bytes, so a 128x128 (or 128x256) single-CTA tile needs more
+// operand bytes in flight per MMA-cycle than shared memory can hold against the TMA latency
+// (measured: 3 stages, tensor pipe 41 % busy).  A CTA pair computes a 256(M) x 256(N) tile with
+// UMMA M=256: each CTA stages only ITS 128 rows of A and ITS 128 rows (half of N) of W_hi/W_lo
+// -> 48 KiB of TMA traffic per 1536 MMA-cycles per SM instead of 80 KiB, and W's L2->SM traffic halves.
+//
+// Per CTA (320 threads):
+//   warp 0     TMA producer: A rows -> local a_full[s];  W_hi/W_lo half -> the LEADER's w_full[s]
+//              (cp.async.bulk.tensor .cta_group::2, peer bit masked)
+//   warp 1     TMEM alloc (both CTAs, cta_group::2); in the leader: single-thread tcgen05.mma issue,
+//              tcgen05.commit multicast -> empty[s] / tmem_full[acc] of BOTH CTAs
+//   warps 2-5  transform: split the A stage into tf32 hi / lo in shared memory, fence.proxy.async,
+//              arrive (remote for the peer) on the leader's ready[s]
+//   warps 6-9  epilogue: tcgen05.ld the 128 x 256 accumulator half, bias / residual / GEGLU, coalesced
+//              stores; arrive on the leader's tmem_empty[acc].  Accumulators are double-buffered in
+//              TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// Tiles are walked m-fastest so the 74 concurrently running clusters share one W tile in L2.
+#include "omt_common.cuh"
+#include <cuda.h>
+
+namespace omt {
+namespace tc2 {
+
+constexpr int BM = 128;                     // rows per CTA (tile M = 256 per pair)
+constexpr int BN = 256;                     // tile N per pair; each CTA stages BN/2 rows of W
+constexpr int BK = 32;
+constexpr int A_BYTES = BM * BK * 4;        // 16 KiB
+constexpr int W_BYTES = (BN / 2) * BK * 4;  // 16 KiB per CTA
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // A, A_lo, W_hi, W_lo
+constexpr int STAGES = 3;
+constexpr int STG_BYTES = 4 * 32 * 33 * 4;  // epilogue transpose staging, one slab per warp
+constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024;
+constexpr int THREADS = 320;
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on a barrier that may live in the peer CTA (cluster-space address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) break;
+    if ((it & 0x3ff) == 0x3ff && clock64() - t0 > 4000000000LL) __trap();   // protocol bug -> trap, never hang
+  }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// W half: data lands in THIS CTA's smem, the transaction bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ CUtensorMap tmWlo, const GemmArgs g, const int epilogue,
+                const int num_m_blk, const int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t a_full[STAGES];      // local: this CTA's A stage landed
+  __shared__ __align__(8) uint64_t w_full[STAGES];      // used in the leader: both W halves landed
+  __shared__ __align__(8) uint64_t ready[STAGES];       // used in the leader: both CTAs' transforms done
+  __shared__ __align__(8) uint64_t empty[STAGES];       // local: MMAs reading this stage retired (multicast commit)
+  __shared__ __align__(8) uint64_t tmem_full[2];        // local: accumulator complete (multicast commit)
+  __shared__ __align__(8) uint64_t tmem_empty[2];       // used in the leader: both epilogues drained the accumulator
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_kb = g.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&w_full[s], 1);
+      mbar_init(&ready[s], 8);        // 4 transform warps x 2 CTAs
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);   // 4 epilogue warps x 2 CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                     // peer barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile % num_m_blk) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile / num_m_blk) * BN + (int)rank * (BN / 2);
+        int c1[2], c2[2];
+        for (int hf = 0; hf < 2; ++hf) {
+          const int r = m0 + hf * 64;
+          if (g.a_seg > 0) { c1[hf] = r % g.a_seg; c2[hf] = r / g.a_seg; }
+          else { c1[hf] = r; c2[hf] = 0; }
+        }
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sp = stage_ptr(s);
+          mbar_expect_tx(&a_full[s], A_BYTES);
+          tma_load_3d(&tmA, &a_full[s], sp, kb * BK, c1[0], c2[0]);
+          tma_load_3d(&tmA, &a_full[s], sp + A_BYTES / 2, kb * BK, c1[1], c2[1]);
+          if (leader) mbar_expect_tx(&w_full[s], 4 * W_BYTES);          // hi + lo from both CTAs
+          tma_load_2d_pair(&tmW, &w_full[s], sp + 2 * A_BYTES, kb * BK, n0);
+          tma_load_2d_pair(&tmWlo, &w_full[s], sp + 2 * A_BYTES + W_BYTES, kb * BK, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA, one thread) =================
+    if (leader && lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
+        const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&w_full[s], ph);
+          mbar_wait(&ready[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_ptr(s));
+          const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + A_BYTES);
+          const uint64_t d_whi = make_desc(sa + 2 * A_BYTES), d_wlo = make_desc(sa + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            mma_tf32_pair(d_tmem, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
+            mma_tf32_pair(d_tmem, d_ahi + adv, d_wlo + adv, IDESC, 1);
+            mma_tf32_pair(d_tmem, d_ahi + adv, d_whi + adv, IDESC, 1);
+          }
+          tc_commit_pair(&empty[s]);
+        }
+        tc_commit_pair(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ================= transform: A -> tf32 hi (in place) + lo =================
+    const int t = threadIdx.x - 64;   // 0..127
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&a_full[s], ph);
+        float4* a = reinterpret_cast<float4*>(stage_ptr(s));
+        float4* alo = reinterpret_cast<float4*>(stage_ptr(s) + A_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = t + i * 128;
+          const float4 v = a[idx];
+          float4 hi, lo;
+          hi.x = tf32_rn(v.x); hi.y = tf32_rn(v.y); hi.z = tf32_rn(v.z); hi.w = tf32_rn(v.w);
+          lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+          a[idx] = hi;
+          alo[idx] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&ready[s]), 0));
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;                            // TMEM lane quarter of this warp (warps 6..9 -> 2,3,0,1)
+    float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + q * (32 * 33);
+    uint32_t tcount = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
+      const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+      const int m0 = (tile % num_m_blk) * (2 * BM) + (int)rank * BM;
+      const int n0 = (tile / num_m_blk) * BN;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= g.N) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int rl = i8 * 4 + (lane >> 3), col = (lane & 7) * 4;
+          const int m = m0 + q * 32 + rl, n = n0 + c * 32 + col;
+          if (m < g.M && n < g.N) {
+            const float* sp = stg + rl * 33 + col;
+            float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            if (g.bias != nullptr) {
+              const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
+              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            }
+            const long long prow = map_row(m, g.c_seg, g.c_seg_stride, g.c_seg_off);
+            if (epilogue == OMT_EPI_GEGLU) {
+              float2 o;
+              o.x = gelu_erf(v.y) * v.x;
+              o.y = gelu_erf(v.w) * v.z;
+              *reinterpret_cast<float2*>(g.C + prow * g.ldc + (n >> 1)) = o;
+            } else {
+              if (g.residual != nullptr) {
+                const float4 rr = *reinterpret_cast<const float4*>(g.residual + prow * g.ldr + n);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              *reinterpret_cast<float4*>(g.C + prow * g.ldc + n) = v;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tmem_empty[acc]), 0));
+    }
+  }
+  // ---- teardown: nobody may leave while the peer can still signal our barriers / read our smem
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return OMT_E_CUDA; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return OMT_E_CUDA; }
+  return OMT_OK;
+}
+
+}  // namespace tc2
+
+int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st) {
+  using namespace tc2;
+  OMT_REQUIRE(g.K % BK == 0 && g.lda % 4 == 0, "omt_linear(tcgen05 v2): K=%d must be a multiple of 32", g.K);
+  if (g.a_seg > 0) {
+    OMT_REQUIRE(g.a_seg % 64 == 0 && g.M % g.a_seg == 0, "omt_linear(tcgen05 v2): A row-map segment %d must be a multiple of 64 dividing M=%d", g.a_seg, g.M);
+  }
+  const int n_pad = (g.N + 127) / 128 * 128;
+  CUtensorMap tmA, tmW, tmWlo;
+  {
+    const int seg = g.a_seg > 0 ? g.a_seg : g.M;
+    const int nseg = g.a_seg > 0 ? g.M / g.a_seg : 1;
+    const long long sstride = g.a_seg > 0 ? g.a_seg_stride : g.M;
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)seg, (cuuint64_t)nseg};
+    cuuint64_t strides[2] = {(cuuint64_t)g.lda * 4, (cuuint64_t)sstride * g.lda * 4};
+    cuuint32_t box[3] = {BK, 64, 1};
+    const float* base = g.A + (size_t)(g.a_seg > 0 ? g.a_seg_off : 0) * g.lda;
+    int rc = encode_map(&tmA, base, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)g.K * 4};
+    cuuint32_t box[2] = {BK, BN / 2};
+    int rc = encode_map(&tmW, g.W, 2, dims, strides, box);
+    if (rc) return rc;
+    rc = encode_map(&tmWlo, W_lo, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool attr = false;
+  if (!attr) {
+    OMT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr = true;
+  }
+  const int num_m_blk = (g.M + 2 * BM - 1) / (2 * BM);
+  const int num_n_blk = (g.N + BN - 1) / BN;
+  const int num_tiles = num_m_blk * num_n_blk;
+  int clusters = omt::sm_count() / 2;
+  if (clusters > num_tiles) clusters = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, tmA, tmW, tmWlo, g, epilogue, num_m_blk, num_tiles));
+  return OMT_OK;
+}
+
+}  // namespace omt

@@ -30,13 +30,19 @@ if mode == "ncu":
     sys.exit(0)
 
 res = {}
-for bn in (128, 256):
-    _cabi.set_option("tc_block_n", bn)
+for bn in (128, 256, 2):
+    if bn == 2:
+        _cabi.set_option("tc_kernel", 2)
+    else:
+        _cabi.set_option("tc_kernel", 1)
+        _cabi.set_option("tc_block_n", bn)
     for name, (N, K, epi) in shapes.items():
         A = torch.randn(M, K, device=dev); C = torch.empty(M, N, device=dev)
         whi, wlo, w = make(N, K)
         for math, mname in ((_cabi.MATH_3XTF32, "3xtf32"), (_cabi.MATH_TF32, "tf32"), (_cabi.MATH_FP32, "fp32")):
-            if math == _cabi.MATH_FP32 and bn == 256:
+            if math == _cabi.MATH_FP32 and bn != 128:
+                continue
+            if bn == 2 and math != _cabi.MATH_3XTF32:
                 continue
             ts = []
             for i in range(7):

@@ -26,10 +26,13 @@ def _pad128(w):
     return L.pad_rows(w, 128)
 
 
-@pytest.mark.parametrize("M,N,K", [(64, 512, 512), (320, 192, 512), (1024, 1024, 768), (200, 512, 192)])
-@pytest.mark.parametrize("math", ["fp32", "3xtf32", "tf32"])
+@pytest.mark.parametrize("M,N,K", [(64, 512, 512), (320, 192, 512), (1024, 1024, 768), (200, 512, 192),
+                                   (4160, 2752, 512)])
+@pytest.mark.parametrize("math", ["fp32", "3xtf32", "3xtf32-v1", "tf32"])
 def test_linear_plain_bias_residual(cuda, M, N, K, math):
     cabi = _cabi()
+    cabi.set_option("tc_kernel", 1 if math.endswith("-v1") else 2)
+    math = math.replace("-v1", "")
     from omnitokenizer_b200 import layout as L
     if math != "fp32" and (K % 32 or M % 64):
         pytest.skip("tcgen05 path needs K % 32 == 0 and 64-row granularity")
@@ -50,9 +53,11 @@ def test_linear_plain_bias_residual(cuda, M, N, K, math):
     assert err < tol, f"{math} M{M} N{N} K{K}: max err {err:.3e}"
 
 
-@pytest.mark.parametrize("math", ["fp32", "3xtf32"])
+@pytest.mark.parametrize("math", ["fp32", "3xtf32", "3xtf32-v1"])
 def test_linear_geglu_and_rowmaps(cuda, math):
     cabi = _cabi()
+    cabi.set_option("tc_kernel", 1 if math.endswith("-v1") else 2)
+    math = math.replace("-v1", "")
     from omnitokenizer_b200 import layout as L
     M, K, inner = 256, 512, 1365
     ku = L.round_up(inner, 32)
