@@ -201,7 +201,10 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if os.environ.get("OMT_BENCH_BATCH"):        # diagnostic: per-GPU load of an N-GPU strong-scaling run on one GPU
+        wl["shape"] = (int(os.environ["OMT_BENCH_BATCH"]),) + wl["shape"][1:]
+        wl["desc"] += f" [batch overridden to {wl['shape'][0]}]"
     shape = wl["shape"]
     B = shape[0]
     is_image = len(shape) == 4

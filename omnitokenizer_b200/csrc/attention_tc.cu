@@ -1,0 +1,422 @@
+// Spatial (full, non-causal) attention core on the tcgen05 tensor cores with 3xTF32 compensation:
+//   O = softmax(scale * Q K^T) V   per (sequence, head), head dim 64, N % 128 == 0.
+// (reference: F.scaled_dot_product_attention at modules/attention.py:451; q, k already carry
+//  rope + l2norm + per-dim scale from omt_qk_prep.)
+//
+// One CTA = 128 queries of one (sequence, head); keys/values are streamed in tiles of 64.
+//   warp 0      TMA producer: Q once, then K / V tiles straight out of the [M, 1536] QKV buffer
+//               (2-D tensor maps, one 32-column SW128 box per half of the head dim)
+//   warp 1      TMEM alloc + single-thread MMA issue:
+//                 S_j  = Q K_j^T        A = Q (K-major), B = K_j (K-major)          -> TMEM S[j&1]
+//                 O_j  = P_j V_j        A = P_j (K-major, written by the softmax warps),
+//                                       B = V_j as loaded (MN-major descriptor)      -> TMEM O[j&1]
+//               every product is 3 MMAs: lo.hi + hi.lo + hi.hi (tf32 operands, fp32 accumulate)
+//   warps 2-5   transform: split Q, K_j, V_j into tf32 hi (in place) / lo in shared memory
+//   warps 6-9   softmax: one thread per query row; S_j from TMEM, online max / sum in fp32 (exp2),
+//               P_j -> shared memory as tf32 hi / lo, O accumulated in REGISTERS:
+//               O = O * alpha_j + O_j  (O_j read back from TMEM), so no TMEM rescale pass exists.
+#include "omt_common.cuh"
+#include <cuda.h>
+
+namespace omt {
+namespace atc {
+
+constexpr int QT = 128;                 // queries per CTA
+constexpr int KT = 64;                  // keys per tile
+constexpr int D = 64;
+constexpr int Q_BYTES = QT * D * 4;     // 32 KiB (two 16 KiB column halves)
+constexpr int K_BYTES = KT * D * 4;     // 16 KiB
+constexpr int P_BYTES = QT * KT * 4;    // 32 KiB (two 16 KiB key halves)
+// smem map (bytes): Q_hi | Q_lo | K_hi | K_lo | V^T_hi | V^T_lo | P_hi | P_lo | V_raw
+constexpr int OFF_QH = 0, OFF_QL = Q_BYTES, OFF_KH = 2 * Q_BYTES, OFF_KL = OFF_KH + K_BYTES;
+constexpr int OFF_VH = OFF_KL + K_BYTES, OFF_VL = OFF_VH + K_BYTES, OFF_PH = OFF_VL + K_BYTES, OFF_PL = OFF_PH + P_BYTES;
+constexpr int OFF_VR = OFF_PL + P_BYTES;
+constexpr int SMEM = OFF_VR + K_BYTES + 1024;        // 208 KiB + alignment slack
+constexpr int THREADS = 320;
+// tf32 x tf32 -> f32, M=128, N=64; bit 16 = B is MN-major (used for V)
+constexpr uint32_t IDESC_KK = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t IDESC_KMN = IDESC_KK | (1u << 16);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) break;
+    if ((it & 0x3ff) == 0x3ff && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major SW128 tile: rows 128 B apart, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// MN-major SW128 operand: 32-element (128 B) chunks along MN repeat every `lbo` bytes, 8-row K groups every 1024 B
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ float tf32_rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+        "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+        "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr) : "memory");
+}
+
+struct Args {
+  float* o; int ldo;
+  int N;            // tokens per sequence
+  float scale_log2; // scale * log2(e)
+  int dbg;          // debug knob (omt_set_option("attn_debug", n)); 0 in production
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t q_full, q_ready, k_full, k_ready, k_empty, v_full, v_ready, v_empty, vr_free, p_full;
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], o_full[2], o_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int ntiles = a.N / KT;
+  const int row_q0 = seq * a.N + qt * QT;      // first query row in the [M, ld] buffer
+  const int row_k0 = seq * a.N;
+  const int col0 = head * D;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+    mbar_init(&q_full, 1); mbar_init(&q_ready, 4);
+    mbar_init(&k_full, 1); mbar_init(&k_ready, 4); mbar_init(&k_empty, 1);
+    mbar_init(&v_full, 1); mbar_init(&v_ready, 4); mbar_init(&v_empty, 1); mbar_init(&vr_free, 4);
+    mbar_init(&p_full, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tm_s = tmem_base;             // S[2] : 2 x 64 columns
+  const uint32_t tm_o = tmem_base + 128;       // O_j[2] : 2 x 64 columns
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_expect_tx(&q_full, Q_BYTES);
+      tma_load_2d(&tmQ, &q_full, smem + OFF_QH, col0, row_q0);
+      tma_load_2d(&tmQ, &q_full, smem + OFF_QH + Q_BYTES / 2, col0 + 32, row_q0);
+      for (int j = 0; j < ntiles; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(&k_empty, ph ^ 1);
+        mbar_expect_tx(&k_full, K_BYTES);
+        tma_load_2d(&tmK, &k_full, smem + OFF_KH, col0, row_k0 + j * KT);
+        tma_load_2d(&tmK, &k_full, smem + OFF_KH + K_BYTES / 2, col0 + 32, row_k0 + j * KT);
+        mbar_wait(&vr_free, ph ^ 1);
+        mbar_expect_tx(&v_full, K_BYTES);
+        tma_load_2d(&tmV, &v_full, smem + OFF_VR, col0, row_k0 + j * KT);
+        tma_load_2d(&tmV, &v_full, smem + OFF_VR + K_BYTES / 2, col0 + 32, row_k0 + j * KT);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t sb = smem_u32(smem);
+      auto issue_s = [&](int j) {
+        mbar_wait(&k_ready, j & 1);
+        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tm_s + (j & 1) * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {             // halves of the head dim (32 columns = one swizzle row)
+          const uint64_t qh = desc_kmajor(sb + OFF_QH + c * (Q_BYTES / 2)), ql = desc_kmajor(sb + OFF_QL + c * (Q_BYTES / 2));
+          const uint64_t kh = desc_kmajor(sb + OFF_KH + c * (K_BYTES / 2)), kl = desc_kmajor(sb + OFF_KL + c * (K_BYTES / 2));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            mma_tf32(d, ql + adv, kh + adv, IDESC_KK, (c | k) != 0);
+            mma_tf32(d, qh + adv, kl + adv, IDESC_KK, 1);
+            mma_tf32(d, qh + adv, kh + adv, IDESC_KK, 1);
+          }
+        }
+        tc_commit(&s_full[j & 1]);
+        tc_commit(&k_empty);
+      };
+      mbar_wait(&q_ready, 0);
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);       // S of the next tile overlaps the softmax of this one
+        mbar_wait(&p_full, j & 1);
+        mbar_wait(&v_ready, j & 1);
+        mbar_wait(&o_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tm_o + (j & 1) * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {             // halves of the key tile (32 keys = one swizzle row of P)
+          const uint64_t ph_ = desc_kmajor(sb + OFF_PH + c * (P_BYTES / 2)), pl_ = desc_kmajor(sb + OFF_PL + c * (P_BYTES / 2));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            // V^T chunk c: [64 d rows][32 keys] K-major (transposed + split by the transform warps)
+            const uint64_t vh = desc_kmajor(sb + OFF_VH + c * (K_BYTES / 2)) + adv, vl = desc_kmajor(sb + OFF_VL + c * (K_BYTES / 2)) + adv;
+            mma_tf32(d, pl_ + adv, vh, IDESC_KK, (c | k) != 0);
+            mma_tf32(d, ph_ + adv, vl, IDESC_KK, 1);
+            mma_tf32(d, ph_ + adv, vh, IDESC_KK, 1);
+          }
+        }
+        tc_commit(&o_full[j & 1]);
+        tc_commit(&v_empty);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ================= transform: tf32 hi (in place) / lo =================
+    const int t = threadIdx.x - 64;
+    auto split = [&](int off_hi, int off_lo, int bytes) {
+      float4* h = reinterpret_cast<float4*>(smem + off_hi);
+      float4* l = reinterpret_cast<float4*>(smem + off_lo);
+      for (int idx = t; idx < bytes / 16; idx += 128) {
+        const float4 v = h[idx];
+        float4 hi, lo;
+        hi.x = tf32_rn(v.x); hi.y = tf32_rn(v.y); hi.z = tf32_rn(v.z); hi.w = tf32_rn(v.w);
+        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+        h[idx] = hi;
+        l[idx] = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+    };
+    mbar_wait(&q_full, 0);
+    split(OFF_QH, OFF_QL, Q_BYTES);
+    if (lane == 0) mbar_arrive(&q_ready);
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(&k_full, j & 1);
+      split(OFF_KH, OFF_KL, K_BYTES);
+      if (lane == 0) mbar_arrive(&k_ready);
+      // V_j: [keys][d] as landed (SW128 per 32-wide d half) -> V^T [d][keys] K-major hi / lo
+      mbar_wait(&v_full, j & 1);
+      mbar_wait(&v_empty, (j & 1) ^ 1);          // P.V of tile j-1 no longer reads the V^T buffers
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * 128 + t;
+        const int key = idx & 63, d4 = idx >> 6;            // a warp = 32 consecutive keys, one d quad
+        const float4 v = *reinterpret_cast<const float4*>(smem + OFF_VR + (d4 >> 3) * (K_BYTES / 2) + key * 128 +
+                                                          (((d4 & 7) ^ (key & 7)) << 4));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+        const int c = key >> 5, kk = key & 31;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int d = d4 * 4 + i;
+          const int off = c * (K_BYTES / 2) + d * 128 + ((((kk >> 2) ^ (d & 7)) << 4) | ((kk & 3) << 2));
+          const float hi = tf32_rn(e[i]);
+          *reinterpret_cast<float*>(smem + OFF_VH + off) = hi;
+          *reinterpret_cast<float*>(smem + OFF_VL + off) = e[i] - hi;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&v_ready); mbar_arrive(&vr_free); }
+    }
+  } else {
+    // ================= softmax + output accumulation =================
+    const int q = warp & 3;                        // TMEM lane quarter
+    const int r = q * 32 + lane;                   // query row inside the tile
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float o_acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    for (int j = 0; j < ntiles; ++j) {
+      float s[KT];
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      tmem_ld32(tm_s + lane_addr + (j & 1) * 64, s);
+      tmem_ld32(tm_s + lane_addr + (j & 1) * 64 + 32, s + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+      float mx = s[0];
+#pragma unroll
+      for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f((m_run - m_new) * a.scale_log2);
+      float psum = 0.f;
+#pragma unroll
+      for (int i = 0; i < KT; ++i) { s[i] = exp2f((s[i] - m_new) * a.scale_log2); psum += s[i]; }
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+      // fold the previous tile's P.V (also proves the P buffer is free again)
+      if (j > 0) {
+        const int jp = j - 1;
+        mbar_wait(&o_full[jp & 1], (jp >> 1) & 1);
+        tc_fence_after();
+        float oj[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          tmem_ld32(tm_o + lane_addr + (jp & 1) * 64 + hh * 32, oj);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[hh * 32 + i] = fmaf(o_acc[hh * 32 + i], alpha_prev, oj[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[jp & 1]);
+      }
+      alpha_prev = alpha;
+      // P_j -> smem (K-major SW128: row r, 16-byte unit u of key-half c at (u ^ (r & 7)))
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint8_t* ph_ = smem + OFF_PH + c * (P_BYTES / 2) + r * 128;
+        uint8_t* pl_ = smem + OFF_PL + c * (P_BYTES / 2) + r * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float4 hi, lo;
+          const float* sv = s + c * 32 + u * 4;
+          hi.x = tf32_rn(sv[0]); hi.y = tf32_rn(sv[1]); hi.z = tf32_rn(sv[2]); hi.w = tf32_rn(sv[3]);
+          lo.x = sv[0] - hi.x; lo.y = sv[1] - hi.y; lo.z = sv[2] - hi.z; lo.w = sv[3] - hi.w;
+          const int su = (u ^ (r & 7)) * 16;
+          *reinterpret_cast<float4*>(ph_ + su) = hi;
+          *reinterpret_cast<float4*>(pl_ + su) = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full);
+    }
+    // last tile's P.V
+    {
+      const int jp = ntiles - 1;
+      mbar_wait(&o_full[jp & 1], (jp >> 1) & 1);
+      tc_fence_after();
+      float oj[32];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        tmem_ld32(tm_o + lane_addr + (jp & 1) * 64 + hh * 32, oj);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[hh * 32 + i] = fmaf(o_acc[hh * 32 + i], alpha_prev, oj[i]);
+      }
+      tc_fence_before();
+    }
+    float inv = 1.0f / l_run;
+    if (a.dbg == 3) { inv = 1.0f; o_acc[0] = l_run; o_acc[1] = m_run; o_acc[2] = alpha_prev; }
+    float* op = a.o + (size_t)(row_q0 + r) * a.ldo + col0;
+#pragma unroll
+    for (int i = 0; i < D; i += 4)
+      *reinterpret_cast<float4*>(op + i) = make_float4(o_acc[i] * inv, o_acc[i + 1] * inv, o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode2d(CUtensorMap* m, const float* base, int cols, long long rows, int ld, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return OMT_E_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return OMT_E_CUDA; }
+  return OMT_OK;
+}
+
+}  // namespace atc
+
+int g_attn_debug = 0;
+
+int launch_attn_tc(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo,
+                   int n_seq, int N, int heads, float scale, cudaStream_t st) {
+  using namespace atc;
+  CUtensorMap tmQ, tmK, tmV;
+  const long long rows = (long long)n_seq * N;
+  int rc = encode2d(&tmQ, q, heads * D, rows, ldq, QT);
+  if (rc) return rc;
+  rc = encode2d(&tmK, k, heads * D, rows, ldk, KT);
+  if (rc) return rc;
+  rc = encode2d(&tmV, v, heads * D, rows, ldv, KT);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    OMT_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr = true;
+  }
+  Args a{o, ldo, N, scale * 1.4426950408889634f, g_attn_debug};
+  dim3 grid(N / QT, heads, n_seq);
+  attn_tc_kernel<<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, a);
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
+}  // namespace omt

@@ -89,9 +89,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  // round-to-nearest (ties away) on the 13 dropped mantissa bits == cvt.rna.tf32.f32 for finite x,
+  // but 2 integer ops instead of the ~7-instruction sequence ptxas emits for the cvt
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -384,8 +384,16 @@ int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math,
 
 }  // namespace omt
 
+namespace omt { extern int g_attn_kernel; extern int g_attn_debug; }
+
 extern "C" int omt_set_option(const char* name, int value) {
   if (name == nullptr) return OMT_E_ARG;
+  if (strcmp(name, "attn_debug") == 0) { omt::g_attn_debug = value; return OMT_OK; }
+  if (strcmp(name, "attn_kernel") == 0) {
+    if (value != 1 && value != 2) { omt::set_error("attn_kernel must be 1 or 2"); return OMT_E_ARG; }
+    omt::g_attn_kernel = value;
+    return OMT_OK;
+  }
   if (strcmp(name, "tc_block_n") == 0) {
     if (value != 128 && value != 256) { omt::set_error("tc_block_n must be 128 or 256"); return OMT_E_ARG; }
     omt::g_tc_bn = value;

@@ -1,0 +1,40 @@
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from omnitokenizer_b200 import _cabi
+_cabi.load(); _cabi.set_option("attn_kernel", 2)
+dev = torch.device("cuda:0")
+N, nseq, H = 128, 1, 8
+M = N * nseq
+def run(q, k, v):
+    qkv = torch.cat([q, k, v], dim=1).contiguous().to(dev)
+    p = qkv.data_ptr()
+    o = torch.full((M, 512), float("nan"), device=dev)
+    _cabi.call("omt_attn_spatial", p, 1536, p + 2048, 1536, p + 4096, 1536, o, 512, nseq, N, H, 8.0)
+    torch.cuda.synchronize()
+    return o.cpu()
+def ref(q, k, v):
+    qq, kk, vv = (t.view(nseq, N, H, 64).permute(0, 2, 1, 3).double() for t in (q, k, v))
+    w = torch.softmax(qq @ kk.transpose(-1, -2) * 8.0, dim=-1) @ vv
+    return w.permute(0, 2, 1, 3).reshape(M, 512).float()
+dbg = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+_cabi.set_option("attn_debug", dbg)
+print("=== dbg", dbg)
+g = torch.Generator().manual_seed(0)
+rnd = lambda: (torch.rand(M, 512, generator=g) - 0.5) * 0.5
+z = torch.zeros(M, 512)
+# A: V = 1 -> O must be 1 whatever S is
+o = run(rnd(), rnd(), torch.ones(M, 512)); print("A  V=1           max|o-1| =", (o - 1).abs().max().item())
+# B: Q = 0 -> uniform P -> O = mean_k V
+v = rnd(); o = run(z, rnd(), v); print("B  Q=0 rand V    err =", (o - ref(z, z, v)).abs().max().item())
+# B2: V[key, d] = key index
+v = torch.arange(M).float().view(M, 1).expand(M, 512).contiguous() % N
+o = run(z, z, v); print("B2 V=key         o[0,:4] =", o[0, :4].tolist(), "want", ref(z, z, v)[0, 0].item())
+# B3: V[key, d] = d index within head
+v = (torch.arange(512) % 64).float().view(1, 512).expand(M, 512).contiguous()
+o = run(z, z, v); print("B3 V=d           o[0,:8] =", o[0, :8].tolist(), " o[0,32:36] =", o[0, 32:36].tolist())
+# C: V = 1-hot on key 5 with peaked S?  general random
+q, k, v = rnd(), rnd(), rnd()
+o = run(q, k, v); r = ref(q, k, v); print("C  random        err =", (o - r).abs().max().item())
+# D: S path only: V = key index, check argmax-ish weighting: k = q (self-peaked)
+q = rnd() * 4; v = torch.arange(M).float().view(M, 1).expand(M, 512).contiguous() % N
+o = run(q, q, v); r = ref(q, q, v); print("D  k=q V=key     err =", (o - r).abs().max().item(), o[3, 0].item(), r[3, 0].item())

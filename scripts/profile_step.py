@@ -10,6 +10,8 @@ os.environ["OMT_MATH"] = math
 dev = torch.device("cuda:0")
 m = bench.make_model(dev)
 shape = bench.WORKLOADS[wl]["shape"]
+if os.environ.get("OMT_BENCH_BATCH"):
+    shape = (int(os.environ["OMT_BENCH_BATCH"]),) + shape[1:]
 x = (torch.rand(shape, generator=torch.Generator().manual_seed(1234)) - 0.5).to(dev)
 is_image = len(shape) == 4
 for _ in range(2):
