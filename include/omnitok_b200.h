@@ -66,6 +66,13 @@ int omt_linear(const float* A, int lda, int a_seg, int a_seg_stride, int a_seg_o
                const float* bias, const float* residual, int ldr,
                int epilogue, int math, omt_stream_t stream);
 
+/* Dual-A form: C[:, :n_split] = A1 . W[:n_split]^T and C[:, n_split:] = A2 . W[n_split:]^T in ONE launch.
+ * Attention.forward projects q from the LayerNormed input and k, v from the RAW input
+ * (attention.py:407-412); stacking [Wq; Wkv] and switching the A tensor map per output tile fuses the two
+ * nn.Linear calls without changing either result.  n_split % 256 == 0; same lda for A1 and A2. */
+int omt_linear2(const float* A1, const float* A2, int n_split, int lda, const float* W, const float* W_lo,
+                float* C, int ldc, int M, int N, int K, int math, omt_stream_t stream);
+
 /* y[r,:] = (x[r,:] - mean) * rstd * w + b over C channels (C % 4 == 0, C <= 1024); b may be NULL.
  * attention.py:73-80 (LayerNorm, beta buffer), :163 (nn.LayerNorm in FeedForward), :688 (norm_out).
  * x may alias y.  (seg, seg_stride, seg_off) is a row map applied to BOTH x and y (patch embed:

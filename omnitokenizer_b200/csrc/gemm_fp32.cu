@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256, 2) gemm_fp32_kernel(const GemmArgs g) {
   const int lrow = tid >> 1, lkq = (tid & 1) * 4;
   int am = m0 + lrow;
   if (am >= g.M) am = g.M - 1;
-  const float* aptr = g.A + map_row(am, g.a_seg, g.a_seg_stride, g.a_seg_off) * g.lda + lkq;
+  const float* abase = (g.A2 != nullptr && n0 >= g.n_split) ? g.A2 : g.A;
+  const float* aptr = abase + map_row(am, g.a_seg, g.a_seg_stride, g.a_seg_off) * g.lda + lkq;
   const float* wptr = g.W + (size_t)(n0 + lrow) * g.K + lkq;   // W rows are padded to a BN multiple
 
   float acc[8][8];
@@ -112,13 +113,13 @@ int launch_gemm_fp32(const GemmArgs& g, int epilogue, cudaStream_t st) {
   return OMT_OK;
 }
 
-int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math, cudaStream_t st);
+int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math, cudaStream_t st, const float* A2, int n_split);
 
 }  // namespace omt
 
 using namespace omt;
 
-extern "C" int omt_linear(const float* A, int lda, int a_seg, int a_seg_stride, int a_seg_off,
+static int linear_impl(const float* A, const float* A2, int n_split, int lda, int a_seg, int a_seg_stride, int a_seg_off,
                           const float* W, const float* W_lo, float* C, int ldc, int c_seg, int c_seg_stride,
                           int c_seg_off, int M, int N, int K, const float* bias, const float* residual,
                           int ldr, int epilogue, int math, omt_stream_t stream) {
@@ -132,13 +133,28 @@ extern "C" int omt_linear(const float* A, int lda, int a_seg, int a_seg_stride, 
   OMT_REQUIRE(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C | (uintptr_t)bias | (uintptr_t)residual) % 16 == 0,
               "omt_linear: pointers must be 16-byte aligned");
   if (M == 0) return OMT_OK;
+  OMT_REQUIRE(A2 == nullptr || (n_split > 0 && n_split % 128 == 0 && (uintptr_t)A2 % 16 == 0), "omt_linear2: bad n_split / A2");
   GemmArgs g{A, lda, a_seg, a_seg_stride, a_seg_off, W, C, ldc, c_seg, c_seg_stride, c_seg_off,
-             M, N, K, bias, residual, ldr};
+             M, N, K, bias, residual, ldr, A2, n_split};
   if (math == OMT_MATH_FP32) return launch_gemm_fp32(g, epilogue, (cudaStream_t)stream);
   if (math == OMT_MATH_3XTF32 || math == OMT_MATH_TF32) {
     OMT_REQUIRE(math == OMT_MATH_TF32 || W_lo != nullptr, "omt_linear: 3xTF32 needs W_lo");
-    return launch_gemm_tc(g, W_lo, epilogue, math, (cudaStream_t)stream);
+    return launch_gemm_tc(g, W_lo, epilogue, math, (cudaStream_t)stream, A2, n_split);
   }
   set_error("omt_linear: unknown math mode %d", math);
   return OMT_E_ARG;
+}
+
+extern "C" int omt_linear(const float* A, int lda, int a_seg, int a_seg_stride, int a_seg_off,
+                          const float* W, const float* W_lo, float* C, int ldc, int c_seg, int c_seg_stride,
+                          int c_seg_off, int M, int N, int K, const float* bias, const float* residual,
+                          int ldr, int epilogue, int math, omt_stream_t stream) {
+  return linear_impl(A, nullptr, 0, lda, a_seg, a_seg_stride, a_seg_off, W, W_lo, C, ldc, c_seg, c_seg_stride, c_seg_off,
+                     M, N, K, bias, residual, ldr, epilogue, math, stream);
+}
+
+extern "C" int omt_linear2(const float* A1, const float* A2, int n_split, int lda, const float* W, const float* W_lo,
+                           float* C, int ldc, int M, int N, int K, int math, omt_stream_t stream) {
+  return linear_impl(A1, A2, n_split, lda, 0, 0, 0, W, W_lo, C, ldc, 0, 0, 0, M, N, K, nullptr, nullptr, 0, OMT_EPI_NONE,
+                     math, stream);
 }

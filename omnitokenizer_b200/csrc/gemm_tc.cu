@@ -342,9 +342,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensor
 static int g_tc_bn = 128;   // tile-N selector of the v1 kernel (set through omt_set_option for tuning)
 static int g_tc_kernel = 2; // 2 = persistent 2-CTA kernel (gemm_tc2.cu) for 3xTF32, 1 = one-tile-per-CTA kernel
 
-int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st);
+int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st, const float* A2, int n_split);
 
-int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math, cudaStream_t st) {
+int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math, cudaStream_t st, const float* A2, int n_split) {
   using namespace tc;
   OMT_REQUIRE(g.K % BK == 0, "omt_linear(tcgen05): K=%d must be a multiple of 32", g.K);
   OMT_REQUIRE(g.lda % 4 == 0, "omt_linear(tcgen05): lda %% 4");
@@ -352,7 +352,8 @@ int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math,
     OMT_REQUIRE(g.a_seg % 64 == 0 && g.M % g.a_seg == 0, "omt_linear(tcgen05): A row-map segment %d must be a multiple of 64 dividing M=%d", g.a_seg, g.M);
   }
   const bool split = (math == OMT_MATH_3XTF32);
-  if (split && g_tc_kernel == 2) return launch_gemm_tc2(g, W_lo, epilogue, st);
+  if (split && g_tc_kernel == 2) return launch_gemm_tc2(g, W_lo, epilogue, st, A2, n_split);
+  OMT_REQUIRE(A2 == nullptr, "omt_linear2: the dual-A form needs the v2 tcgen05 kernel or the fp32 path");
   const int n_pad = (g.N + 127) / 128 * 128;
   CUtensorMap tmA, tmW, tmWlo;
   {

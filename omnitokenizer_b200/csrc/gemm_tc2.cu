@@ -15,7 +15,7 @@
 //              tcgen05.commit multicast -> empty[s] / tmem_full[acc] of BOTH CTAs
 //   warps 2-5  transform: split the A stage into tf32 hi / lo in shared memory, fence.proxy.async,
 //              arrive (remote for the peer) on the leader's ready[s]
-//   warps 6-9  epilogue: tcgen05.ld the 128 x 256 accumulator half, bias / residual / GEGLU, coalesced
+//   warps 6-13 epilogue: tcgen05.ld the 128 x 256 accumulator half, bias / residual / GEGLU, coalesced
 //              stores; arrive on the leader's tmem_empty[acc].  Accumulators are double-buffered in
 //              TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 // Tiles are walked m-fastest so the 74 concurrently running clusters share one W tile in L2.
@@ -32,9 +32,10 @@ constexpr int A_BYTES = BM * BK * 4;        // 16 KiB
 constexpr int W_BYTES = (BN / 2) * BK * 4;  // 16 KiB per CTA
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // A, A_lo, W_hi, W_lo
 constexpr int STAGES = 3;
-constexpr int STG_BYTES = 4 * 32 * 33 * 4;  // epilogue transpose staging, one slab per warp
+constexpr int EPI_WARPS = 8;                // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int STG_BYTES = EPI_WARPS * 32 * 33 * 4;  // epilogue transpose staging, one slab per warp
 constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024;
-constexpr int THREADS = 320;
+constexpr int THREADS = 192 + EPI_WARPS * 32;   // TMA, MMA, 4 transform warps, 8 epilogue warps
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
 
@@ -127,9 +128,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                const __grid_constant__ CUtensorMap tmWlo, const GemmArgs g, const int epilogue,
-                const int num_m_blk, const int num_tiles) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, const GemmArgs g,
+                const int epilogue, const int num_m_blk, const int num_tiles, const int n_split) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t a_full[STAGES];      // local: this CTA's A stage landed
@@ -148,6 +149,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
@@ -158,7 +160,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);   // 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);   // epilogue warps of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -181,6 +183,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile % num_m_blk) * (2 * BM) + (int)rank * BM;
         const int n0 = (tile / num_m_blk) * BN + (int)rank * (BN / 2);
+        const CUtensorMap* mapA = (n0 < n_split) ? &tmA : &tmA2;     // dual-A: columns >= n_split read the second matrix
         int c1[2], c2[2];
         for (int hf = 0; hf < 2; ++hf) {
           const int r = m0 + hf * 64;
@@ -193,8 +196,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sp = stage_ptr(s);
           mbar_expect_tx(&a_full[s], A_BYTES);
-          tma_load_3d(&tmA, &a_full[s], sp, kb * BK, c1[0], c2[0]);
-          tma_load_3d(&tmA, &a_full[s], sp + A_BYTES / 2, kb * BK, c1[1], c2[1]);
+          tma_load_3d(mapA, &a_full[s], sp, kb * BK, c1[0], c2[0]);
+          tma_load_3d(mapA, &a_full[s], sp + A_BYTES / 2, kb * BK, c1[1], c2[1]);
           if (leader) mbar_expect_tx(&w_full[s], 4 * W_BYTES);          // hi + lo from both CTAs
           tma_load_2d_pair(&tmW, &w_full[s], sp + 2 * A_BYTES, kb * BK, n0);
           tma_load_2d_pair(&tmWlo, &w_full[s], sp + 2 * A_BYTES + W_BYTES, kb * BK, n0);
@@ -261,49 +264,65 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ================= epilogue =================
-    const int q = warp & 3;                            // TMEM lane quarter of this warp (warps 6..9 -> 2,3,0,1)
-    float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + q * (32 * 33);
+    const int q = warp & 3;                            // TMEM lane quarter this warp may read
+    const int hf = (warp - 6) >> 2;                    // which half of the tile's columns
+    float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 6) * (32 * 33);
+    const int rl0 = lane >> 3, col = (lane & 7) * 4;
     uint32_t tcount = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
       const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
       const int m0 = (tile % num_m_blk) * (2 * BM) + (int)rank * BM;
       const int n0 = (tile / num_m_blk) * BN;
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n0 + c * 32 >= g.N) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
-        __syncwarp();
+      // residual rows are prefetched one 32-column chunk ahead so their latency hides behind the TMEM read
+      float4 res[2][8];
+      auto load_res = [&](int c, float4* dst) {
 #pragma unroll
         for (int i8 = 0; i8 < 8; ++i8) {
-          const int rl = i8 * 4 + (lane >> 3), col = (lane & 7) * 4;
-          const int m = m0 + q * 32 + rl, n = n0 + c * 32 + col;
-          if (m < g.M && n < g.N) {
-            const float* sp = stg + rl * 33 + col;
-            float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
-            if (g.bias != nullptr) {
-              const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
-              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-            }
-            const long long prow = map_row(m, g.c_seg, g.c_seg_stride, g.c_seg_off);
-            if (epilogue == OMT_EPI_GEGLU) {
-              float2 o;
-              o.x = gelu_erf(v.y) * v.x;
-              o.y = gelu_erf(v.w) * v.z;
-              *reinterpret_cast<float2*>(g.C + prow * g.ldc + (n >> 1)) = o;
-            } else {
-              if (g.residual != nullptr) {
-                const float4 rr = *reinterpret_cast<const float4*>(g.residual + prow * g.ldr + n);
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+          const int m = m0 + q * 32 + i8 * 4 + rl0, n = n0 + c * 32 + col;
+          dst[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.residual != nullptr && m < g.M && n < g.N)
+            dst[i8] = *reinterpret_cast<const float4*>(g.residual + map_row(m, g.c_seg, g.c_seg_stride, g.c_seg_off) * g.ldr + n);
+        }
+      };
+      load_res(hf * 4, res[0]);
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = hf * 4 + ci;
+        if (n0 + c * 32 < g.N) {
+          if (ci + 1 < 4) load_res(c + 1, res[(ci + 1) & 1]);
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int rl = i8 * 4 + rl0;
+            const int m = m0 + q * 32 + rl, n = n0 + c * 32 + col;
+            if (m < g.M && n < g.N) {
+              const float* sp = stg + rl * 33 + col;
+              float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+              if (g.bias != nullptr) {
+                const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
               }
-              *reinterpret_cast<float4*>(g.C + prow * g.ldc + n) = v;
+              const long long prow = map_row(m, g.c_seg, g.c_seg_stride, g.c_seg_off);
+              if (epilogue == OMT_EPI_GEGLU) {
+                float2 o;
+                o.x = gelu_erf(v.y) * v.x;
+                o.y = gelu_erf(v.w) * v.z;
+                *reinterpret_cast<float2*>(g.C + prow * g.ldc + (n >> 1)) = o;
+              } else {
+                const float4 rr = res[ci & 1][i8];
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+                *reinterpret_cast<float4*>(g.C + prow * g.ldc + n) = v;
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -345,14 +364,15 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 
 }  // namespace tc2
 
-int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st) {
+int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st, const float* A2, int n_split) {
   using namespace tc2;
   OMT_REQUIRE(g.K % BK == 0 && g.lda % 4 == 0, "omt_linear(tcgen05 v2): K=%d must be a multiple of 32", g.K);
   if (g.a_seg > 0) {
     OMT_REQUIRE(g.a_seg % 64 == 0 && g.M % g.a_seg == 0, "omt_linear(tcgen05 v2): A row-map segment %d must be a multiple of 64 dividing M=%d", g.a_seg, g.M);
   }
   const int n_pad = (g.N + 127) / 128 * 128;
-  CUtensorMap tmA, tmW, tmWlo;
+  CUtensorMap tmA, tmA2, tmW, tmWlo;
+  if (A2 != nullptr) OMT_REQUIRE(n_split > 0 && n_split % BN == 0, "omt_linear2: n_split=%d must be a multiple of 256", n_split);
   {
     const int seg = g.a_seg > 0 ? g.a_seg : g.M;
     const int nseg = g.a_seg > 0 ? g.M / g.a_seg : 1;
@@ -362,6 +382,9 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
     cuuint32_t box[3] = {BK, 64, 1};
     const float* base = g.A + (size_t)(g.a_seg > 0 ? g.a_seg_off : 0) * g.lda;
     int rc = encode_map(&tmA, base, 3, dims, strides, box);
+    if (rc) return rc;
+    const float* base2 = (A2 != nullptr ? A2 : g.A) + (size_t)(g.a_seg > 0 ? g.a_seg_off : 0) * g.lda;
+    rc = encode_map(&tmA2, base2, 3, dims, strides, box);
     if (rc) return rc;
   }
   {
@@ -392,7 +415,8 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, tmA, tmW, tmWlo, g, epilogue, num_m_blk, num_tiles));
+  OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_tiles,
+                              A2 != nullptr ? n_split : 0x7fffffff));
   return OMT_OK;
 }
 

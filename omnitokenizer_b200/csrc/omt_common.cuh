@@ -65,6 +65,7 @@ struct GemmArgs {
   float* C; int ldc; int c_seg, c_seg_stride, c_seg_off;
   int M, N, K;
   const float* bias; const float* residual; int ldr;
+  const float* A2; int n_split;   // dual-A form: output columns >= n_split are computed from A2 (same lda / row map)
 };
 
 }  // namespace omt

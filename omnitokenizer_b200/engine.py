@@ -123,8 +123,8 @@ class Engine:
             ap = lp + ".1"
             d["norm_g"], d["norm_b"] = f32(sd[ap + ".norm.gamma"]), f32(sd[ap + ".norm.beta"])
             d["q_scale"], d["k_scale"] = f32(sd[ap + ".q_scale"]), f32(sd[ap + ".k_scale"])
-            d["to_q"] = lin(ap + ".to_q", bias=False)
-            d["to_kv"] = lin(ap + ".to_kv", bias=False)
+            # [Wq; Wkv] stacked: one dual-A GEMM writes q | k | v into the QKV buffer
+            d["to_qkv"] = PackedLinear(torch.cat([sd[ap + ".to_q.weight"], sd[ap + ".to_kv.weight"]], dim=0), None, dev, m)
             d["to_out"] = lin(ap + ".to_out", bias=False)
             ff(d, lp + ".3")
             return d
@@ -217,8 +217,9 @@ class Engine:
                            int(self.causal_peg))
                 ws.X, ws.Y = ws.Y, ws.X
                 self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
-                self._linear(ws.XN, C, lyr["to_q"], q_ptr, ld3, M)            # q from the normalised input
-                self._linear(ws.X, C, lyr["to_kv"], k_ptr, ld3, M)            # k, v from the RAW input (attention.py:407)
+                # q from the normalised input, k / v from the RAW input (attention.py:407-412), one launch
+                wq = lyr["to_qkv"]
+                _cabi.call("omt_linear2", ws.XN, ws.X, C, C, wq.w, wq.w_lo, q_ptr, ld3, M, wq.n, wq.k, wq.math)
                 cos = sin = None
                 if (not temporal) and self.rope:
                     cos, sin = self._table(("rope", N), lambda: L.rope_tables(N, self.dh))

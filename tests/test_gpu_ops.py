@@ -303,3 +303,23 @@ def test_errors_are_loud(cuda):
         cabi.call("omt_layernorm", x, 512, x, 512, x, None, 4, 514, 1e-5, 0, 0, 0)
     with pytest.raises(RuntimeError, match="omt_attn_spatial"):
         cabi.call("omt_attn_spatial", x, 512, x, 512, x, 512, x, 512, 1, 100, 8, 8.0)
+
+
+@pytest.mark.parametrize("math", ["fp32", "3xtf32"])
+def test_linear2_dual_a(cuda, math):
+    """q from LN(x), k/v from raw x in one launch (attention.py:407-412)."""
+    cabi = _cabi()
+    cabi.set_option("tc_kernel", 2)
+    from omnitokenizer_b200 import layout as L
+    M, K = 640, 512
+    A1, A2, Wt = _rand((M, K), 70), _rand((M, K), 71), _rand((1536, K), 72, 0.05)
+    ref = torch.cat([A1.double() @ Wt[:512].double().t(), A2.double() @ Wt[512:].double().t()], dim=1).float()
+    Wp = _pad128(Wt).to(cuda)
+    Wlo = None
+    mode = cabi.MATH_FP32
+    if math == "3xtf32":
+        hi = L.tf32_round(Wp)
+        Wlo, Wp, mode = (Wp - hi).contiguous(), hi, cabi.MATH_3XTF32
+    out = torch.full((M, 1536), float("nan"), device=cuda)
+    cabi.call("omt_linear2", A1.to(cuda), A2.to(cuda), 512, K, Wp, Wlo, out, 1536, M, 1536, K, mode)
+    assert (out.cpu() - ref).abs().max().item() < 2e-5
