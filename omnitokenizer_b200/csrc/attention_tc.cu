@@ -27,11 +27,11 @@ constexpr int D = 64;
 constexpr int Q_BYTES = QT * D * 4;     // 32 KiB (two 16 KiB column halves)
 constexpr int K_BYTES = KT * D * 4;     // 16 KiB
 constexpr int P_BYTES = QT * KT * 4;    // 32 KiB (two 16 KiB key halves)
-// smem map (bytes): Q_hi | Q_lo | K_hi | K_lo | V^T_hi | V^T_lo | P_hi | P_lo | V_raw
+// smem map (bytes): Q_hi | Q_lo | K_hi | K_lo | V^T_hi | V^T_lo | P_hi | P_lo | V_raw | K_raw
 constexpr int OFF_QH = 0, OFF_QL = Q_BYTES, OFF_KH = 2 * Q_BYTES, OFF_KL = OFF_KH + K_BYTES;
 constexpr int OFF_VH = OFF_KL + K_BYTES, OFF_VL = OFF_VH + K_BYTES, OFF_PH = OFF_VL + K_BYTES, OFF_PL = OFF_PH + P_BYTES;
-constexpr int OFF_VR = OFF_PL + P_BYTES;
-constexpr int SMEM = OFF_VR + K_BYTES + 1024;        // 208 KiB + alignment slack
+constexpr int OFF_VR = OFF_PL + P_BYTES, OFF_KR = OFF_VR + K_BYTES;   // TMA landing buffers (raw fp32)
+constexpr int SMEM = OFF_KR + K_BYTES + 1024;        // 224 KiB + alignment slack
 constexpr int THREADS = 320;
 // tf32 x tf32 -> f32, M=128, N=64; bit 16 = B is MN-major (used for V)
 constexpr uint32_t IDESC_KK = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -119,7 +119,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmV, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t q_full, q_ready, k_full, k_ready, k_empty, v_full, v_ready, v_empty, vr_free, p_full;
+  __shared__ __align__(8) uint64_t q_full, q_ready, k_full, k_ready, k_empty, v_full, v_ready, v_empty, vr_free, kr_free, p_full;
   __shared__ __align__(8) uint64_t s_full[2], s_empty[2], o_full[2], o_empty[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -136,7 +136,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
     mbar_init(&q_full, 1); mbar_init(&q_ready, 4);
     mbar_init(&k_full, 1); mbar_init(&k_ready, 4); mbar_init(&k_empty, 1);
-    mbar_init(&v_full, 1); mbar_init(&v_ready, 4); mbar_init(&v_empty, 1); mbar_init(&vr_free, 4);
+    mbar_init(&v_full, 1); mbar_init(&v_ready, 4); mbar_init(&v_empty, 1); mbar_init(&vr_free, 4); mbar_init(&kr_free, 4);
     mbar_init(&p_full, 4);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
@@ -163,10 +163,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tma_load_2d(&tmQ, &q_full, smem + OFF_QH + Q_BYTES / 2, col0 + 32, row_q0);
       for (int j = 0; j < ntiles; ++j) {
         const uint32_t ph = j & 1;
-        mbar_wait(&k_empty, ph ^ 1);
+        mbar_wait(&kr_free, ph ^ 1);             // K_j lands in the raw buffer while S_{j-1} is still running
         mbar_expect_tx(&k_full, K_BYTES);
-        tma_load_2d(&tmK, &k_full, smem + OFF_KH, col0, row_k0 + j * KT);
-        tma_load_2d(&tmK, &k_full, smem + OFF_KH + K_BYTES / 2, col0 + 32, row_k0 + j * KT);
+        tma_load_2d(&tmK, &k_full, smem + OFF_KR, col0, row_k0 + j * KT);
+        tma_load_2d(&tmK, &k_full, smem + OFF_KR + K_BYTES / 2, col0 + 32, row_k0 + j * KT);
         mbar_wait(&vr_free, ph ^ 1);
         mbar_expect_tx(&v_full, K_BYTES);
         tma_load_2d(&tmV, &v_full, smem + OFF_VR, col0, row_k0 + j * KT);
@@ -245,10 +245,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_wait(&q_full, 0);
     split(OFF_QH, OFF_QL, Q_BYTES);
     if (lane == 0) mbar_arrive(&q_ready);
+    // K_{j+1} is split BEFORE V_j is transposed: its operand buffers free up as soon as S_j retires, whereas
+    // V^T must wait for P.V of tile j-1 -- doing them in tile order serialised S_{j+1} behind that wait.
+    auto split_k = [&](int jj) {
+      mbar_wait(&k_full, jj & 1);
+      mbar_wait(&k_empty, (jj & 1) ^ 1);          // S_{j-1} no longer reads the K hi / lo operand buffers
+      {
+        const float4* src = reinterpret_cast<const float4*>(smem + OFF_KR);
+        float4* h = reinterpret_cast<float4*>(smem + OFF_KH);
+        float4* l = reinterpret_cast<float4*>(smem + OFF_KL);
+#pragma unroll
+        for (int i = 0; i < K_BYTES / 16 / 128; ++i) {
+          const int idx = t + i * 128;
+          const float4 v = src[idx];
+          float4 hi, lo;
+          hi.x = tf32_rn(v.x); hi.y = tf32_rn(v.y); hi.z = tf32_rn(v.z); hi.w = tf32_rn(v.w);
+          lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+          h[idx] = hi;
+          l[idx] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+      }
+      if (lane == 0) { mbar_arrive(&k_ready); mbar_arrive(&kr_free); }
+    };
+    split_k(0);
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(&k_full, j & 1);
-      split(OFF_KH, OFF_KL, K_BYTES);
-      if (lane == 0) mbar_arrive(&k_ready);
+      if (j + 1 < ntiles) split_k(j + 1);
       // V_j: [keys][d] as landed (SW128 per 32-wide d half) -> V^T [d][keys] K-major hi / lo
       mbar_wait(&v_full, j & 1);
       mbar_wait(&v_empty, (j & 1) ^ 1);          // P.V of tile j-1 no longer reads the V^T buffers

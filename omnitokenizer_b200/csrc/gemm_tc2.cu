@@ -127,10 +127,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr) : "memory");
 }
 
+// Tile raster: clusters walk the tiles in groups of G = num_clusters m-blocks; inside a group all clusters
+// take the same n-block at the same time, so a group's slice of A (G x 256 rows, ~40 MB for K=512) and W stay
+// L2-resident across the n sweep instead of re-streaming A from HBM once per n-block (measured 7.5x re-read).
+__device__ __forceinline__ void decode_tile(int linear, int num_m_blk, int num_n_blk, int G, int& m_blk, int& n_blk) {
+  const int per_group = G * num_n_blk;
+  const int g = linear / per_group;
+  const int m_lo = g * G;
+  const int gm = min(G, num_m_blk - m_lo);          // m-blocks in this (possibly last, smaller) group
+  const int r = linear - g * per_group;
+  n_blk = r / gm;
+  m_blk = m_lo + r % gm;
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, const GemmArgs g,
-                const int epilogue, const int num_m_blk, const int num_tiles, const int n_split) {
+                const int epilogue, const int num_m_blk, const int num_n_blk, const int n_split) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t a_full[STAGES];      // local: this CTA's A stage landed
@@ -146,6 +159,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_kb = g.K / BK;
+  const int num_tiles = num_m_blk * num_n_blk;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -181,8 +195,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile % num_m_blk) * (2 * BM) + (int)rank * BM;
-        const int n0 = (tile / num_m_blk) * BN + (int)rank * (BN / 2);
+        int m_blk, n_blk;
+        decode_tile(tile, num_m_blk, num_n_blk, num_clusters, m_blk, n_blk);
+        const int m0 = m_blk * (2 * BM) + (int)rank * BM;
+        const int n0 = n_blk * BN + (int)rank * (BN / 2);
         const CUtensorMap* mapA = (n0 < n_split) ? &tmA : &tmA2;     // dual-A: columns >= n_split read the second matrix
         int c1[2], c2[2];
         for (int hf = 0; hf < 2; ++hf) {
@@ -271,8 +287,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t tcount = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
       const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
-      const int m0 = (tile % num_m_blk) * (2 * BM) + (int)rank * BM;
-      const int n0 = (tile / num_m_blk) * BN;
+      int m_blk, n_blk;
+      decode_tile(tile, num_m_blk, num_n_blk, num_clusters, m_blk, n_blk);
+      const int m0 = m_blk * (2 * BM) + (int)rank * BM;
+      const int n0 = n_blk * BN;
       // residual rows are prefetched one 32-column chunk ahead so their latency hides behind the TMEM read
       float4 res[2][8];
       auto load_res = [&](int c, float4* dst) {
@@ -415,7 +433,7 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_tiles,
+  OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk,
                               A2 != nullptr ? n_split : 0x7fffffff));
   return OMT_OK;
 }

@@ -259,22 +259,41 @@ __global__ void __launch_bounds__(256) peg_tile_kernel(const float* __restrict__
   const int pad_lo = causal ? 2 : 1;
   const int rows = (TT + 2) * (HB + 2);
   const int nth = blockDim.x;
-  // ---- stage the halo tile
-  const int total4 = rows * (w + 2) * (PEG_CC / 4);
-  for (int i = threadIdx.x; i < total4; i += nth) {
-    const int c4 = i & 3;
-    int pos = i >> 2;
-    const int pw = pos % (w + 2); pos /= (w + 2);
-    const int ph = pos % (HB + 2);
-    const int pt = pos / (HB + 2);
+  // ---- halo tile: the (few) integer divisions happen once per (plane,row) pair and once per position,
+  //      not once per 16-byte load: int2 {global row or -1, smem float offset} per position
+  int2* pmap = reinterpret_cast<int2*>(tile + rows * RS);
+  const int P = rows * (w + 2);
+  for (int pos = threadIdx.x; pos < P; pos += nth) {
+    const int pw = pos % (w + 2);
+    const int pr = pos / (w + 2);
+    const int ph = pr % (HB + 2), pt = pr / (HB + 2);
     const int t2 = t0 - pad_lo + pt, h2 = h0 - 1 + ph, w2 = pw - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int row = -1;
     if (t2 >= 0 && t2 < T && h2 >= 0 && h2 < h && w2 >= 0 && w2 < w) {
       const int f = (t2 * h + h2) * w + w2;
-      const int row = temporal ? (f % T) * N + f / T : f;
-      v = __ldg(reinterpret_cast<const float4*>(x + (bbase + row) * C + c0) + c4);
+      row = temporal ? (f % T) * N + f / T : f;
     }
-    *reinterpret_cast<float4*>(tile + (pt * (HB + 2) + ph) * RS + pw * PEG_CC + c4 * 4) = v;
+    pmap[pos] = make_int2(row, pr * RS + pw * PEG_CC);
+  }
+  __syncthreads();
+  // gathers are issued in batches of 8 per thread before any shared store so ~8 x 16 B are in flight per thread
+  for (int i0 = threadIdx.x; i0 < P * 4; i0 += nth * 8) {
+    float4 v[8];
+    int so[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * nth;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      so[u] = -1;
+      if (i < P * 4) {
+        const int2 pm = pmap[i >> 2];
+        so[u] = pm.y + (i & 3) * 4;
+        if (pm.x >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(x + (bbase + pm.x) * C + c0) + (i & 3));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (so[u] >= 0) *reinterpret_cast<float4*>(tile + so[u]) = v[u];
   }
   __syncthreads();
   // ---- strips
@@ -295,6 +314,7 @@ __global__ void __launch_bounds__(256) peg_tile_kernel(const float* __restrict__
     win[r9][2] = *reinterpret_cast<const float2*>(rp + PEG_CC);
   }
   const int fbase = ((t0 + st) * h + (h0 + sh)) * w;
+  int tau = fbase % T, nn = fbase / T;               // temporal: volume position f <-> canonical (tau, n), advanced incrementally
   for (int w2 = 0; w2 < w; ++w2) {
     float2 acc = bb;
 #pragma unroll
@@ -310,9 +330,9 @@ __global__ void __launch_bounds__(256) peg_tile_kernel(const float* __restrict__
     }
     const float2 ctr = causal ? win[7][1] : win[4][1];   // the un-shifted token itself (residual)
     acc.x += ctr.x; acc.y += ctr.y;
-    const int f = fbase + w2;
-    const int row = temporal ? (f % T) * N + f / T : f;
+    const int row = temporal ? tau * N + nn : fbase + w2;
     *reinterpret_cast<float2*>(y + (bbase + row) * C + c0 + 2 * cp) = acc;
+    if (++tau == T) { tau = 0; ++nn; }
   }
 }
 
@@ -486,9 +506,9 @@ extern "C" int omt_peg_volume(const float* x, float* y, const float* w27, const 
   int RS = (w + 2) * PEG_CC;
   RS += ((16 - RS % 32) + 32) % 32;                  // row stride == 16 (mod 32) floats: 2-way minimum bank pattern
   int TT = T < 5 ? T : 5, HB = 4;
-  auto smem_of = [&](int tt, int hb) { return (size_t)(tt + 2) * (hb + 2) * RS * sizeof(float); };
-  while (HB > 1 && (smem_of(TT, HB) > 100 * 1024 || TT * HB * 8 > 256)) --HB;
-  while (TT > 1 && (smem_of(TT, HB) > 100 * 1024 || TT * HB * 8 > 256)) --TT;
+  auto smem_of = [&](int tt, int hb) { return (size_t)(tt + 2) * (hb + 2) * (RS * sizeof(float) + (size_t)(w + 2) * 8); };
+  while (HB > 1 && (smem_of(TT, HB) > 112 * 1024 || TT * HB * 8 > 256)) --HB;
+  while (TT > 1 && (smem_of(TT, HB) > 112 * 1024 || TT * HB * 8 > 256)) --TT;
   const size_t smem = smem_of(TT, HB);
   OMT_REQUIRE(smem <= 200 * 1024, "omt_peg_volume: row of %d tokens does not fit the shared-memory tile", w);
   static size_t smem_set = 0;
