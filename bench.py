@@ -222,11 +222,13 @@ def main():
             codes = torch.empty((0,), dtype=torch.int64, device=dev)
         else:
             codes = m.encode(x, is_image)
-        if world > 1:
-            all_codes = od.all_gather_codes(codes, B)       # the single collective
-        if x.shape[0] == 0:
-            return None
-        return m.decode(codes, is_image)
+        pending = None
+        if world > 1 and not os.environ.get("OMT_BENCH_NO_GATHER"):
+            pending = od.all_gather_codes_async(codes, B)   # the single collective, overlapped with the local decode
+        rec = None if x.shape[0] == 0 else m.decode(codes, is_image)
+        if pending is not None:
+            all_codes = pending.wait()                      # every rank now holds the full (B,T',h,w) index tensor
+        return rec
 
     def barrier():
         if world > 1:

@@ -45,6 +45,7 @@ int omt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* GEMM epilogue selectors */
 #define OMT_EPI_NONE 0
 #define OMT_EPI_GEGLU 1   /* packed columns (2j, 2j+1) = (value, gate): C[:, j] = gelu_erf(gate) * value */
+#define OMT_EPI_QKV 2     /* omt_linear2 only: rope + l2norm + scale on the q / k heads (attention.py:417-437) */
 
 /* GEMM math selectors */
 #define OMT_MATH_FP32 0      /* CUDA-core FFMA, exact fp32 (parity anchor) */
@@ -71,7 +72,12 @@ int omt_linear(const float* A, int lda, int a_seg, int a_seg_stride, int a_seg_o
  * (attention.py:407-412); stacking [Wq; Wkv] and switching the A tensor map per output tile fuses the two
  * nn.Linear calls without changing either result.  n_split % 256 == 0; same lda for A1 and A2. */
 int omt_linear2(const float* A1, const float* A2, int n_split, int lda, const float* W, const float* W_lo,
-                float* C, int ldc, int M, int N, int K, int math, omt_stream_t stream);
+                float* C, int ldc, int M, int N, int K, int math,
+                /* optional fused q/k preparation (what omt_qk_prep does), q_scale == NULL disables it:
+                 * columns [0, qk_cols) are heads of 64; the first half carry q (q_scale), the second k (k_scale);
+                 * rope tables [tokens, 32] or NULL; the rope position of row m is m % tokens */
+                const float* q_scale, const float* k_scale, const float* rope_cos, const float* rope_sin,
+                int qk_cols, int tokens, omt_stream_t stream);
 
 /* y[r,:] = (x[r,:] - mean) * rstd * w + b over C channels (C % 4 == 0, C <= 1024); b may be NULL.
  * attention.py:73-80 (LayerNorm, beta buffer), :163 (nn.LayerNorm in FeedForward), :688 (norm_out).

@@ -119,7 +119,9 @@ int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math,
 
 using namespace omt;
 
-static int linear_impl(const float* A, const float* A2, int n_split, int lda, int a_seg, int a_seg_stride, int a_seg_off,
+struct QkPrep { const float* q_scale; const float* k_scale; const float* cos; const float* sin; int qk_cols; int tokens; };
+
+static int linear_impl(const QkPrep* qk, const float* A, const float* A2, int n_split, int lda, int a_seg, int a_seg_stride, int a_seg_off,
                           const float* W, const float* W_lo, float* C, int ldc, int c_seg, int c_seg_stride,
                           int c_seg_off, int M, int N, int K, const float* bias, const float* residual,
                           int ldr, int epilogue, int math, omt_stream_t stream) {
@@ -127,7 +129,7 @@ static int linear_impl(const float* A, const float* A2, int n_split, int lda, in
   OMT_REQUIRE(A && W && C, "omt_linear: null pointer");
   OMT_REQUIRE(M >= 0 && N > 0 && K > 0, "omt_linear: bad shape M=%d N=%d K=%d", M, N, K);
   OMT_REQUIRE(K % 8 == 0 && lda % 4 == 0 && ldc % 4 == 0 && N % 4 == 0, "omt_linear: K %% 8, lda/ldc/N %% 4 required (K=%d lda=%d ldc=%d N=%d)", K, lda, ldc, N);
-  OMT_REQUIRE(epilogue == OMT_EPI_NONE || epilogue == OMT_EPI_GEGLU, "omt_linear: unknown epilogue %d", epilogue);
+  OMT_REQUIRE(epilogue == OMT_EPI_NONE || epilogue == OMT_EPI_GEGLU || epilogue == OMT_EPI_QKV, "omt_linear: unknown epilogue %d", epilogue);
   OMT_REQUIRE(!(epilogue == OMT_EPI_GEGLU && residual), "omt_linear: GEGLU epilogue takes no residual");
   OMT_REQUIRE(residual == nullptr || ldr % 4 == 0, "omt_linear: ldr %% 4 required");
   OMT_REQUIRE(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C | (uintptr_t)bias | (uintptr_t)residual) % 16 == 0,
@@ -135,8 +137,12 @@ static int linear_impl(const float* A, const float* A2, int n_split, int lda, in
   if (M == 0) return OMT_OK;
   OMT_REQUIRE(A2 == nullptr || (n_split > 0 && n_split % 128 == 0 && (uintptr_t)A2 % 16 == 0), "omt_linear2: bad n_split / A2");
   GemmArgs g{A, lda, a_seg, a_seg_stride, a_seg_off, W, C, ldc, c_seg, c_seg_stride, c_seg_off,
-             M, N, K, bias, residual, ldr, A2, n_split};
-  if (math == OMT_MATH_FP32) return launch_gemm_fp32(g, epilogue, (cudaStream_t)stream);
+             M, N, K, bias, residual, ldr, A2, n_split, nullptr, nullptr, nullptr, nullptr, 0, 1};
+  if (qk != nullptr) {
+    g.rope_cos = qk->cos; g.rope_sin = qk->sin; g.q_scale = qk->q_scale; g.k_scale = qk->k_scale;
+    g.qk_cols = qk->qk_cols; g.tokens = qk->tokens;
+  }
+  if (math == OMT_MATH_FP32) return launch_gemm_fp32(g, epilogue == OMT_EPI_QKV ? OMT_EPI_NONE : epilogue, (cudaStream_t)stream);
   if (math == OMT_MATH_3XTF32 || math == OMT_MATH_TF32) {
     OMT_REQUIRE(math == OMT_MATH_TF32 || W_lo != nullptr, "omt_linear: 3xTF32 needs W_lo");
     return launch_gemm_tc(g, W_lo, epilogue, math, (cudaStream_t)stream, A2, n_split);
@@ -149,12 +155,27 @@ extern "C" int omt_linear(const float* A, int lda, int a_seg, int a_seg_stride, 
                           const float* W, const float* W_lo, float* C, int ldc, int c_seg, int c_seg_stride,
                           int c_seg_off, int M, int N, int K, const float* bias, const float* residual,
                           int ldr, int epilogue, int math, omt_stream_t stream) {
-  return linear_impl(A, nullptr, 0, lda, a_seg, a_seg_stride, a_seg_off, W, W_lo, C, ldc, c_seg, c_seg_stride, c_seg_off,
+  return linear_impl(nullptr, A, nullptr, 0, lda, a_seg, a_seg_stride, a_seg_off, W, W_lo, C, ldc, c_seg, c_seg_stride, c_seg_off,
                      M, N, K, bias, residual, ldr, epilogue, math, stream);
 }
 
+namespace omt { int tc_fuses_qkprep(int math); }   // gemm_tc.cu: does the selected tcgen05 kernel apply OMT_EPI_QKV itself?
+
 extern "C" int omt_linear2(const float* A1, const float* A2, int n_split, int lda, const float* W, const float* W_lo,
-                           float* C, int ldc, int M, int N, int K, int math, omt_stream_t stream) {
-  return linear_impl(A1, A2, n_split, lda, 0, 0, 0, W, W_lo, C, ldc, 0, 0, 0, M, N, K, nullptr, nullptr, 0, OMT_EPI_NONE,
-                     math, stream);
+                           float* C, int ldc, int M, int N, int K, int math, const float* q_scale,
+                           const float* k_scale, const float* rope_cos, const float* rope_sin, int qk_cols, int tokens,
+                           omt_stream_t stream) {
+  if (q_scale == nullptr)
+    return linear_impl(nullptr, A1, A2, n_split, lda, 0, 0, 0, W, W_lo, C, ldc, 0, 0, 0, M, N, K, nullptr, nullptr, 0,
+                       OMT_EPI_NONE, math, stream);
+  OMT_REQUIRE(k_scale != nullptr && qk_cols > 0 && qk_cols % 128 == 0 && qk_cols <= N && tokens > 0,
+              "omt_linear2: bad q/k preparation arguments");
+  OMT_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "omt_linear2: cos/sin must both be given");
+  QkPrep qk{q_scale, k_scale, rope_cos, rope_sin, qk_cols, tokens};
+  const bool fused = tc_fuses_qkprep(math);
+  int rc = linear_impl(&qk, A1, A2, n_split, lda, 0, 0, 0, W, W_lo, C, ldc, 0, 0, 0, M, N, K, nullptr, nullptr, 0,
+                       fused ? OMT_EPI_QKV : OMT_EPI_NONE, math, stream);
+  if (rc != OMT_OK || fused) return rc;
+  // kernels without the fused epilogue (fp32 / v1 tcgen05): same arithmetic as a separate pass over q and k
+  return omt_qk_prep(C, ldc, C + qk_cols / 2, ldc, q_scale, k_scale, rope_cos, rope_sin, M, tokens, qk_cols / 2 / 64, stream);
 }

@@ -344,6 +344,8 @@ static int g_tc_kernel = 2; // 2 = persistent 2-CTA kernel (gemm_tc2.cu) for 3xT
 
 int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st, const float* A2, int n_split);
 
+int tc_fuses_qkprep(int math) { return math == OMT_MATH_3XTF32 && g_tc_kernel == 2; }
+
 int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math, cudaStream_t st, const float* A2, int n_split) {
   using namespace tc;
   OMT_REQUIRE(g.K % BK == 0, "omt_linear(tcgen05): K=%d must be a multiple of 32", g.K);

@@ -140,6 +140,8 @@ __device__ __forceinline__ void decode_tile(int linear, int num_m_blk, int num_n
   m_blk = m_lo + r % gm;
 }
 
+template <bool QKV>     // QKV: the epilogue applies rope + l2norm + scale to the q / k heads (separate instantiation so the
+                        // common path's code and register allocation are untouched)
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, const GemmArgs g,
@@ -302,44 +304,128 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             dst[i8] = *reinterpret_cast<const float4*>(g.residual + map_row(m, g.c_seg, g.c_seg_stride, g.c_seg_off) * g.ldr + n);
         }
       };
-      load_res(hf * 4, res[0]);
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
+      // transpose a 32-row x 32-column chunk through the warp's staging slab and store it with 16-byte accesses
+      auto store_chunk = [&](const int c, const uint32_t (&r)[32], const float4 (&rs)[8], const bool use_res) {
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c = hf * 4 + ci;
-        if (n0 + c * 32 < g.N) {
-          if (ci + 1 < 4) load_res(c + 1, res[(ci + 1) & 1]);
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
-          __syncwarp();
-#pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int rl = i8 * 4 + rl0;
-            const int m = m0 + q * 32 + rl, n = n0 + c * 32 + col;
-            if (m < g.M && n < g.N) {
-              const float* sp = stg + rl * 33 + col;
-              float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
-              if (g.bias != nullptr) {
-                const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
-                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-              }
-              const long long prow = map_row(m, g.c_seg, g.c_seg_stride, g.c_seg_off);
-              if (epilogue == OMT_EPI_GEGLU) {
-                float2 o;
-                o.x = gelu_erf(v.y) * v.x;
-                o.y = gelu_erf(v.w) * v.z;
-                *reinterpret_cast<float2*>(g.C + prow * g.ldc + (n >> 1)) = o;
-              } else {
-                const float4 rr = res[ci & 1][i8];
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-                *reinterpret_cast<float4*>(g.C + prow * g.ldc + n) = v;
-              }
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int rl = i8 * 4 + rl0;
+          const int m = m0 + q * 32 + rl, n = n0 + c * 32 + col;
+          if (m < g.M && n < g.N) {
+            const float* sp = stg + rl * 33 + col;
+            float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            if (g.bias != nullptr) {
+              const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
+              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            }
+            const long long prow = map_row(m, g.c_seg, g.c_seg_stride, g.c_seg_off);
+            if (epilogue == OMT_EPI_GEGLU) {
+              float2 o;
+              o.x = gelu_erf(v.y) * v.x;
+              o.y = gelu_erf(v.w) * v.z;
+              *reinterpret_cast<float2*>(g.C + prow * g.ldc + (n >> 1)) = o;
+            } else {
+              if (use_res) { v.x += rs[i8].x; v.y += rs[i8].y; v.z += rs[i8].z; v.w += rs[i8].w; }
+              *reinterpret_cast<float4*>(g.C + prow * g.ldc + n) = v;
             }
           }
-          __syncwarp();
+        }
+        __syncwarp();
+      };
+      if constexpr (QKV) {
+        // ---- q / k heads: rope + l2norm + per-dim scale on the accumulator before it is stored
+        //      (attention.py:417-421, 435-437).  A head = two 32-column chunks; both are transposed through
+        //      the staging slab first so that a row's 64 values sit in 8 lanes x 2 float4 -- table reads and
+        //      stores are then coalesced and the l2 norm is a 3-step shuffle inside each 8-lane group.
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const int c = hf * 4 + pr * 2;
+          const int nh = n0 + c * 32;                         // first column of this head
+          if (nh >= g.N) break;
+          float4 va[8], vb[8];
+          {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32);
+            tmem_ld32(taddr, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const float* sp = stg + (i8 * 4 + rl0) * 33 + col;
+              va[i8] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            }
+            __syncwarp();
+            tmem_ld32(taddr + 32, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const float* sp = stg + (i8 * 4 + rl0) * 33 + col;
+              vb[i8] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            }
+            __syncwarp();
+          }
+          const bool prep = nh < g.qk_cols;
+          float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), sb = sa;
+          if (prep) {
+            const float* scv = (nh < g.qk_cols / 2) ? g.q_scale : g.k_scale;
+            sa = *reinterpret_cast<const float4*>(scv + col);
+            sb = *reinterpret_cast<const float4*>(scv + 32 + col);
+          }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int m = m0 + q * 32 + i8 * 4 + rl0;
+            float4 xa = va[i8], xb = vb[i8];
+            if (prep) {
+              if (g.rope_cos != nullptr) {
+                const int pos = (m < g.M ? m : 0) % g.tokens;
+                const float* ct = g.rope_cos + (size_t)pos * 32 + (col >> 1);
+                const float* st_ = g.rope_sin + (size_t)pos * 32 + (col >> 1);
+                const float2 ca = *reinterpret_cast<const float2*>(ct), sna = *reinterpret_cast<const float2*>(st_);
+                const float2 cb = *reinterpret_cast<const float2*>(ct + 16), snb = *reinterpret_cast<const float2*>(st_ + 16);
+                float4 t;
+                t.x = xa.x * ca.x - xa.y * sna.x; t.y = xa.x * sna.x + xa.y * ca.x;
+                t.z = xa.z * ca.y - xa.w * sna.y; t.w = xa.z * sna.y + xa.w * ca.y;
+                xa = t;
+                t.x = xb.x * cb.x - xb.y * snb.x; t.y = xb.x * snb.x + xb.y * cb.x;
+                t.z = xb.z * cb.y - xb.w * snb.y; t.w = xb.z * snb.y + xb.w * cb.y;
+                xb = t;
+              }
+              float ss = (xa.x * xa.x + xa.y * xa.y) + (xa.z * xa.z + xa.w * xa.w) +
+                         (xb.x * xb.x + xb.y * xb.y) + (xb.z * xb.z + xb.w * xb.w);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+              ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+              const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);     // one division per row instead of 64 (<= 1 ulp vs x / den)
+              xa.x = xa.x * inv * sa.x; xa.y = xa.y * inv * sa.y; xa.z = xa.z * inv * sa.z; xa.w = xa.w * inv * sa.w;
+              xb.x = xb.x * inv * sb.x; xb.y = xb.y * inv * sb.y; xb.z = xb.z * inv * sb.z; xb.w = xb.w * inv * sb.w;
+            }
+            if (m < g.M) {
+              float* crow = g.C + map_row(m, g.c_seg, g.c_seg_stride, g.c_seg_off) * g.ldc + nh + col;
+              *reinterpret_cast<float4*>(crow) = xa;
+              if (nh + 32 + col < g.N) *reinterpret_cast<float4*>(crow + 32) = xb;
+            }
+          }
+        }
+      } else {
+        load_res(hf * 4, res[0]);
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = hf * 4 + ci;
+          if (n0 + c * 32 < g.N) {
+            if (ci + 1 < 4) load_res(c + 1, res[(ci + 1) & 1]);
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+            store_chunk(c, r, res[ci & 1], g.residual != nullptr);
+          }
         }
       }
       tc_fence_before();
@@ -416,7 +502,8 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
   }
   static bool attr = false;
   if (!attr) {
-    OMT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    OMT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    OMT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
   const int num_m_blk = (g.M + 2 * BM - 1) / (2 * BM);
@@ -433,8 +520,11 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk,
-                              A2 != nullptr ? n_split : 0x7fffffff));
+  const int ns = A2 != nullptr ? n_split : 0x7fffffff;
+  if (epilogue == OMT_EPI_QKV)
+    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns));
+  else
+    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<false>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns));
   return OMT_OK;
 }
 

@@ -66,6 +66,9 @@ struct GemmArgs {
   int M, N, K;
   const float* bias; const float* residual; int ldr;
   const float* A2; int n_split;   // dual-A form: output columns >= n_split are computed from A2 (same lda / row map)
+  // OMT_EPI_QKV: heads (64 columns) below qk_cols get rope + l2norm + per-dim scale in the epilogue
+  const float* rope_cos; const float* rope_sin; const float* q_scale; const float* k_scale;
+  int qk_cols; int tokens;        // rope position of row m is m % tokens; columns < qk_cols/2 use q_scale, the rest k_scale
 };
 
 }  // namespace omt

@@ -28,28 +28,52 @@ def shard(x: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = No
     return x[s:e]
 
 
-def all_gather_codes(local_codes: torch.Tensor, batch_total: int, group=None) -> torch.Tensor:
-    """Every rank ends up with the full (B, T', h, w) int64 index tensor.
+class GatheredCodes:
+    """Handle of an in-flight all-gather of code indices: the collective runs on NCCL's stream while the
+    caller keeps enqueueing work (decode does not depend on other ranks' codes); ``wait()`` joins it and
+    returns the full (B, T', h, w) int64 tensor."""
 
-    local_codes: this rank's (b_local, T', h, w) LongTensor (b_local may be 0 or differ by one between
-    ranks).  Codes travel as int32 (n_codes <= 2^31) in a single all_gather_into_tensor; ragged shards
-    are padded to the largest shard and trimmed after the gather."""
+    def __init__(self, work, recv, batch_total, world, per):
+        self._work, self._recv, self._B, self._world, self._per = work, recv, batch_total, world, per
+        self._out = None
+
+    def wait(self) -> torch.Tensor:
+        if self._out is None:
+            if self._work is not None:
+                self._work.wait()          # current stream waits for the collective (no host sync on CUDA)
+            recv = self._recv
+            if self._world > 1 and self._B % self._world != 0:
+                parts = []
+                for r in range(self._world):
+                    s, e = shard_bounds(self._B, r, self._world)
+                    parts.append(recv[r * self._per: r * self._per + (e - s)])
+                recv = torch.cat(parts, dim=0)
+            self._out = recv.to(torch.int64)
+        return self._out
+
+
+def all_gather_codes_async(local_codes: torch.Tensor, batch_total: int, group=None) -> GatheredCodes:
+    """Start the single collective of the path.  Codes travel as int32 (n_codes <= 2^31) in ONE
+    all_gather_into_tensor; ragged shards are padded to the largest shard and trimmed in wait()."""
     world = dist.get_world_size(group)
     if world == 1:
-        return local_codes
+        return GatheredCodes(None, local_codes, batch_total, 1, batch_total)
     per = (batch_total + world - 1) // world
     tail = tuple(local_codes.shape[1:])
-    send = torch.zeros((per,) + tail, dtype=torch.int32, device=local_codes.device)
-    send[: local_codes.shape[0]] = local_codes.to(torch.int32)
+    if local_codes.shape[0] == per:
+        send = local_codes.to(torch.int32)
+    else:
+        send = torch.zeros((per,) + tail, dtype=torch.int32, device=local_codes.device)
+        send[: local_codes.shape[0]] = local_codes.to(torch.int32)
     recv = torch.empty((world * per,) + tail, dtype=torch.int32, device=local_codes.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    if batch_total % world == 0:
-        return recv.to(torch.int64)
-    parts = []
-    for r in range(world):
-        s, e = shard_bounds(batch_total, r, world)
-        parts.append(recv[r * per: r * per + (e - s)])
-    return torch.cat(parts, dim=0).to(torch.int64)
+    work = dist.all_gather_into_tensor(recv, send, group=group, async_op=True)
+    return GatheredCodes(work, recv, batch_total, world, per)
+
+
+def all_gather_codes(local_codes: torch.Tensor, batch_total: int, group=None) -> torch.Tensor:
+    """Every rank ends up with the full (B, T', h, w) int64 index tensor (blocking form).
+    local_codes: this rank's (b_local, T', h, w) LongTensor (b_local may be 0 or differ by one between ranks)."""
+    return all_gather_codes_async(local_codes, batch_total, group).wait()
 
 
 @torch.no_grad()

@@ -176,6 +176,15 @@ class Engine:
         self.n_codes = E.shape[0]
 
     # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def fuse_qkprep(M: int) -> bool:
+        """rope + l2norm + scale inside the QKV GEMM epilogue pays off once the epilogue is hidden behind the next
+        tile's main loop (many tiles per cluster); for small M the separate row-wise kernel is faster."""
+        mode = os.environ.get("OMT_FUSE_QKPREP", "auto")
+        if mode in ("0", "1"):
+            return mode == "1"
+        return M >= 16384
+
     def _workspace(self, M: int) -> Workspace:
         ws = self._ws.get(M)
         if ws is None:
@@ -218,13 +227,19 @@ class Engine:
                 ws.X, ws.Y = ws.Y, ws.X
                 self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
                 # q from the normalised input, k / v from the RAW input (attention.py:407-412), one launch
+                # rope (spatial blocks) + l2norm + q/k scale ride in the same launch (fused GEMM epilogue)
                 wq = lyr["to_qkv"]
-                _cabi.call("omt_linear2", ws.XN, ws.X, C, C, wq.w, wq.w_lo, q_ptr, ld3, M, wq.n, wq.k, wq.math)
                 cos = sin = None
                 if (not temporal) and self.rope:
                     cos, sin = self._table(("rope", N), lambda: L.rope_tables(N, self.dh))
-                _cabi.call("omt_qk_prep", q_ptr, ld3, k_ptr, ld3, lyr["q_scale"], lyr["k_scale"], cos, sin, M, N,
-                           self.heads)
+                if self.fuse_qkprep(M):
+                    _cabi.call("omt_linear2", ws.XN, ws.X, C, C, wq.w, wq.w_lo, q_ptr, ld3, M, wq.n, wq.k, wq.math,
+                               lyr["q_scale"], lyr["k_scale"], cos, sin, 2 * C, N)
+                else:
+                    _cabi.call("omt_linear2", ws.XN, ws.X, C, C, wq.w, wq.w_lo, q_ptr, ld3, M, wq.n, wq.k, wq.math,
+                               None, None, None, None, 0, 0)
+                    _cabi.call("omt_qk_prep", q_ptr, ld3, k_ptr, ld3, lyr["q_scale"], lyr["k_scale"], cos, sin, M, N,
+                               self.heads)
                 if temporal:
                     _cabi.call("omt_attn_temporal", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, ws.O, C, B, T, N, self.heads,
                                8.0, int(self.causal_attn))

@@ -321,5 +321,23 @@ def test_linear2_dual_a(cuda, math):
         hi = L.tf32_round(Wp)
         Wlo, Wp, mode = (Wp - hi).contiguous(), hi, cabi.MATH_3XTF32
     out = torch.full((M, 1536), float("nan"), device=cuda)
-    cabi.call("omt_linear2", A1.to(cuda), A2.to(cuda), 512, K, Wp, Wlo, out, 1536, M, 1536, K, mode)
+    cabi.call("omt_linear2", A1.to(cuda), A2.to(cuda), 512, K, Wp, Wlo, out, 1536, M, 1536, K, mode, None, None, None,
+              None, 0, 0)
     assert (out.cpu() - ref).abs().max().item() < 2e-5
+    # with the fused q/k preparation (rope + l2norm + scale on the q and k heads, v untouched)
+    N = 128
+    qs, ks = _rand((64,), 73, 0.5) + 1.0, _rand((64,), 74, 0.5) + 1.0
+    cos, sin = L.rope_tables(N, 64)
+    for tables in ((cos, sin), (None, None)):
+        out.fill_(float("nan"))
+        cabi.call("omt_linear2", A1.to(cuda), A2.to(cuda), 512, K, Wp, Wlo, out, 1536, M, 1536, K, mode, qs.to(cuda),
+                  ks.to(cuda), None if tables[0] is None else tables[0].to(cuda),
+                  None if tables[1] is None else tables[1].to(cuda), 1024, N)
+        got = out.cpu()
+        for sl, sc in ((slice(0, 512), qs), (slice(512, 1024), ks)):
+            t = ref[:, sl].reshape(M // N, N, 8, 64)
+            if tables[0] is not None:
+                t = oo.apply_rope(t, cos, sin)
+            want = (oo.l2norm(t) * sc).reshape(M, 512)
+            assert (got[:, sl] - want).abs().max().item() < 2e-5
+        assert (got[:, 1024:] - ref[:, 1024:]).abs().max().item() < 2e-5
