@@ -241,7 +241,10 @@ static int launch_temporal(const float* q, int ldq, const float* k, int ldk, con
 
 int launch_attn_tc(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo,
                    int n_seq, int N, int heads, float scale, cudaStream_t st);
-int g_attn_kernel = 2;   // 2 = tcgen05 3xTF32 core (attention_tc.cu) when N % 128 == 0, 1 = CUDA-core fp32
+int launch_attn_tc3(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo,
+                    int n_seq, int N, int heads, float scale, cudaStream_t st);
+int g_attn_kernel = 3;   // N % 128 == 0: 3 = tcgen05 3xTF32, Q / P as TMEM operands (attention_tc3.cu);
+                         // 2 = tcgen05 3xTF32, all operands in smem (attention_tc.cu); 1 = CUDA-core fp32
 
 static int set_flash_smem() {
   static bool done = false;
@@ -274,6 +277,8 @@ extern "C" int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk
   OMT_REQUIRE(N > 0 && N % 64 == 0, "omt_attn_spatial: N=%d must be a multiple of 64", N);
   OMT_REQUIRE(heads > 0 && heads <= 65535 && n_seq <= 65535, "omt_attn_spatial: grid too large");
   if (n_seq == 0) return OMT_OK;
+  if (g_attn_kernel == 3 && N % 128 == 0)
+    return launch_attn_tc3(q, ldq, k, ldk, v, ldv, o, ldo, n_seq, N, heads, scale, (cudaStream_t)stream);
   if (g_attn_kernel == 2 && N % 128 == 0)
     return launch_attn_tc(q, ldq, k, ldk, v, ldv, o, ldo, n_seq, N, heads, scale, (cudaStream_t)stream);
   rc = set_flash_smem();

@@ -1,7 +1,7 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from omnitokenizer_b200 import _cabi
-_cabi.load(); _cabi.set_option("attn_kernel", 2)
+_cabi.load(); _cabi.set_option("attn_kernel", int(os.environ.get("ATTN_KERNEL", 2)))
 dev = torch.device("cuda:0")
 N, nseq, H = 128, 1, 8
 M = N * nseq
@@ -38,3 +38,17 @@ o = run(q, k, v); r = ref(q, k, v); print("C  random        err =", (o - r).abs(
 # D: S path only: V = key index, check argmax-ish weighting: k = q (self-peaked)
 q = rnd() * 4; v = torch.arange(M).float().view(M, 1).expand(M, 512).contiguous() % N
 o = run(q, q, v); r = ref(q, q, v); print("D  k=q V=key     err =", (o - r).abs().max().item(), o[3, 0].item(), r[3, 0].item())
+# timing at the cfg-3 shape
+N, nseq = 1024, 40
+M = N * nseq
+qkv = (torch.rand(M, 1536, device=dev) - 0.5)
+p = qkv.data_ptr(); o = torch.empty(M, 512, device=dev)
+for kern in (1, 2, 3):
+    _cabi.set_option("attn_kernel", kern)
+    ts = []
+    for i in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); _cabi.call("omt_attn_spatial", p, 1536, p + 2048, 1536, p + 4096, 1536, o, 512, nseq, N, H, 8.0); b.record()
+        torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    print(f"attn kernel {kern}: {sorted(ts)[2]*1e3:.0f} us  ({4*N*64*M*8/ (sorted(ts)[2]*1e-3)/1e12:.1f} TFLOP/s algorithmic)")
+

@@ -177,7 +177,7 @@ def _attn_inputs(M, seed):
     return q, k, v, qkv
 
 
-@pytest.mark.parametrize("kernel,N", [(1, 256), (2, 256), (2, 1024), (1, 64)])
+@pytest.mark.parametrize("kernel,N", [(1, 256), (2, 256), (2, 1024), (3, 256), (3, 1024), (1, 64)])
 def test_qk_prep_and_spatial_attention(cuda, kernel, N):
     cabi = _cabi()
     cabi.set_option("attn_kernel", kernel)
@@ -204,7 +204,7 @@ def test_qk_prep_and_spatial_attention(cuda, kernel, N):
     want = torch.softmax((qq.double() @ kk.double().transpose(-1, -2)) * 8.0, dim=-1) @ vv.double()
     want = want.permute(0, 2, 1, 3).reshape(M, 512).float()
     err = (o.cpu() - want).abs().max().item()
-    cabi.set_option("attn_kernel", 2)
+    cabi.set_option("attn_kernel", 3)
     assert err < (5e-6 if kernel == 1 else 1e-5), f"attention kernel {kernel} N={N}: max err {err:.2e}"
 
 
