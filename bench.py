@@ -286,10 +286,20 @@ def main():
         math = default_math()
         tf32_peak = pk["bf16_tflops"] / 2.0
         achieved = k_flops / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": f"gemm_tc_kernel[{math}] FF1+GEGLU M={M_local} N=2730 K=512" if math != "fp32"
-                else f"gemm_fp32_kernel FF1+GEGLU M={M_local} N=2730 K=512",
+        traffic = None
+        try:      # dram__bytes_read+write of this launch from the committed `ncu --set full` capture (cfg-3, N=1)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_ff1_traffic.json")))
+            if world == 1 and args.workload == "cfg3" and not os.environ.get("OMT_BENCH_BATCH") and math == tj.get("math"):
+                traffic = tj["dram_bytes"]
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": f"gemm_tc2_kernel[{math}] FF1+GEGLU M={M_local} N=2730 K=512" if math == "3xtf32"
+                else (f"gemm_tc_kernel[{math}] FF1+GEGLU M={M_local} N=2730 K=512" if math == "tf32"
+                      else f"gemm_fp32_kernel FF1+GEGLU M={M_local} N=2730 K=512"),
                 "achieved": round(achieved, 2), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
-                "frac": round(achieved / tf32_peak, 4), "traffic": None, "ms_per_launch": round(k_ms, 4),
+                "frac": round(achieved / tf32_peak, 4), "traffic": traffic,
+                "algorithmic_bytes": int(M_local * 512 * 4 + 2 * 2752 * 512 * 4 + M_local * 1376 * 4),
+                "ms_per_launch": round(k_ms, 4),
                 "peak_note": f"tf32 dense = 0.5 x {pk_src} bf16 burst {pk['bf16_tflops']} TF/s; FLOPs are algorithmic fp32 "
                              f"(2MNK); 3xTF32 issues 3 MMAs per product so its own ceiling is 1/3 of this",
                 "whole_path": {"tflop_per_batch": TFLOP[args.workload],

@@ -159,7 +159,9 @@ int omt_post_vq(const int64_t* idx, const float* E, const float* zc, const float
 /* Tuning knobs (process-wide).  "tc_kernel" = 2 (default: persistent 2-CTA cta_group::2 kernel for
  * 3xTF32) | 1 (one tile per CTA);  "tc_block_n" = 128 | 256: tile-N of kernel 1;
  * "attn_kernel" = 3 (default: tcgen05 3xTF32 spatial attention core, P as TMEM operand, when N % 128 == 0)
- * | 2 (tcgen05, all operands in shared memory) | 1 (CUDA-core fp32);  "attn_debug": developer knob of kernel 2. */
+ * | 2 (tcgen05, all operands in shared memory) | 1 (CUDA-core fp32);  "attn_debug": developer knob of kernel 2;
+ * "pdl" = 0 (default; measured 2-4 % slower when on) | 1: launch with programmatic dependent launch so a kernel's prologue overlaps the tail of
+ * its predecessor (every kernel executes griddepcontrol.wait before its first global-memory access). */
 int omt_set_option(const char* name, int value);
 
 /* hi/lo split used by the tcgen05 3xTF32 path: lo = x - tf32_trunc(x) (elementwise, n % 4 == 0). */

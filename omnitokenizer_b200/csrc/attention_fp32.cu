@@ -40,6 +40,7 @@ __device__ __forceinline__ long long token_row(const AttnArgs& a, int seq, int i
 
 template <bool WINDOW>
 __global__ void __launch_bounds__(256, 2) attn_flash_kernel(const AttnArgs a) {
+  pdl_sync();
   extern __shared__ __align__(16) float smem[];
   float* Qs = smem;                 // [64][64] swizzled, pre-scaled
   float* Ks = smem + 4096;          // [64][64] swizzled
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) attn_temporal_kernel(const float* __restr
                                                             const float* __restrict__ v, int ldv,
                                                             float* __restrict__ o, int ldo, int B,
                                                             int N, int heads, float scale, int causal) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = (long long)B * N * heads;
@@ -234,7 +236,7 @@ static int launch_temporal(const float* q, int ldq, const float* k, int ldk, con
                            cudaStream_t st) {
   const long long warps = (long long)B * N * heads;
   const unsigned blocks = (unsigned)((warps + 7) / 8);
-  attn_temporal_kernel<T><<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, B, N, heads, scale, causal);
+  OMT_CUDA(launch_k(attn_temporal_kernel<T>, dim3(blocks), dim3(256), 0, st, q, ldq, k, ldk, v, ldv, o, ldo, B, N, heads, scale, causal));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -285,7 +287,7 @@ extern "C" int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk
   if (rc) return rc;
   AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, nullptr, N, 0, 0, 0, scale};
   dim3 grid(N / AQ, heads, n_seq);
-  attn_flash_kernel<false><<<grid, 256, 65536, (cudaStream_t)stream>>>(a);
+  OMT_CUDA(launch_k(attn_flash_kernel<false>, grid, dim3(256), 65536, (cudaStream_t)stream, a));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -306,7 +308,7 @@ extern "C" int omt_attn_window(const float* q, int ldq, const float* k, int ldk,
   if (rc) return rc;
   AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, bias, h * w, h, w, ws, scale};
   dim3 grid((unsigned)n_seq, heads, 1);
-  attn_flash_kernel<true><<<grid, 256, 65536, (cudaStream_t)stream>>>(a);
+  OMT_CUDA(launch_k(attn_flash_kernel<true>, grid, dim3(256), 65536, (cudaStream_t)stream, a));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }

@@ -193,6 +193,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();      // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -472,7 +473,7 @@ int launch_attn_tc3(const float* q, int ldq, const float* k, int ldk, const floa
   }
   Args a{o, ldo, N, scale * 1.4426950408889634f};
   dim3 grid(N / QT, heads, n_seq);
-  attn_tc3_kernel<<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, a);
+  OMT_CUDA(launch_k(attn_tc3_kernel, grid, dim3(THREADS), SMEM, st, tmQ, tmK, tmV, a));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }

@@ -13,6 +13,7 @@ constexpr int LDS_ = 132;   // padded row stride of the transposed tiles (floats
 
 template <int EPI>
 __global__ void __launch_bounds__(256, 2) gemm_fp32_kernel(const GemmArgs g) {
+  pdl_sync();
   __shared__ __align__(16) float As[2][BK * LDS_];
   __shared__ __align__(16) float Ws[2][BK * LDS_];
   const int tid = threadIdx.x;

@@ -391,6 +391,7 @@ namespace omt { extern int g_attn_kernel; extern int g_attn_debug; }
 
 extern "C" int omt_set_option(const char* name, int value) {
   if (name == nullptr) return OMT_E_ARG;
+  if (strcmp(name, "pdl") == 0) { omt::g_pdl = value ? 1 : 0; return OMT_OK; }
   if (strcmp(name, "attn_debug") == 0) { omt::g_attn_debug = value; return OMT_OK; }
   if (strcmp(name, "attn_kernel") == 0) {
     if (value < 1 || value > 3) { omt::set_error("attn_kernel must be 1, 2 or 3"); return OMT_E_ARG; }

@@ -189,6 +189,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync();                     // peer barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();      // prologue above overlapped the previous kernel's tail; no global memory touched before this point
 
   auto stage_ptr = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
 
@@ -516,10 +517,12 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
   const int ns = A2 != nullptr ? n_split : 0x7fffffff;
   if (epilogue == OMT_EPI_QKV)
     OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns));

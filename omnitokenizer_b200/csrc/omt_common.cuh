@@ -38,6 +38,28 @@ int sm_count();
 
 #define OMT_LAUNCH_CHECK() OMT_CUDA(cudaGetLastError())
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every kernel calls pdl_sync() before its first global-memory access: griddepcontrol.wait blocks until the
+// previous kernel in the stream has completed and flushed (a no-op when the launch carried no PDL attribute);
+// launch_dependents then lets the NEXT kernel's CTAs be scheduled as soon as all of ours are resident, so its
+// prologue (barrier init, TMEM alloc, descriptor prefetch, launch latency) overlaps our last wave.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+extern int g_pdl;   // omt_set_option("pdl", 0|1)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

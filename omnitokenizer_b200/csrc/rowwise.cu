@@ -15,6 +15,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int g_pdl = 0;   // measured on B200: PDL made the step 2-4 % slower (dependent CTAs hold SM resources during the tail), so it is opt-in
 static int g_dev_ok[64];   // 0 unknown, 1 ok, -1 bad
 static int g_sms[64];
 
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ b, int M, int C,
                                                         float eps, int seg, int seg_stride, int seg_off) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int lrow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (lrow >= M) return;
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
                                                           const float* __restrict__ lb, int rows,
                                                           int Cin, int T, int H, int W, int p, int pt,
                                                           int first, float eps) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict
                                                          float* __restrict__ video, long long total4,
                                                          int Cin, int T, int H, int W, int p, int pt,
                                                          int first) {
+  pdl_sync();
   const int hh = H / p, ww = W / p;
   const int PT = first ? 1 : pt;
   const int K4 = Cin * PT * p * p / 4;
@@ -200,6 +204,7 @@ __global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, f
                                                   const float* __restrict__ bias,
                                                   const int32_t* __restrict__ nbr, int rows_per_b,
                                                   int C, long long M) {
+  pdl_sync();
   extern __shared__ float4 wsm[];   // [27][C/4]
   __shared__ int32_t nsm[PEG_ROWS][27];
   const int c4 = threadIdx.x;       // channel group
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(256) peg_tile_kernel(const float* __restrict__
                                                        const float* __restrict__ w27,
                                                        const float* __restrict__ bias, int T, int h, int w,
                                                        int C, int temporal, int causal, int TT, int HB, int RS) {
+  pdl_sync();
   extern __shared__ __align__(16) float tile[];      // [(TT+2)][(HB+2)] rows of RS floats ((w+2)*16 + pad)
   const int N = h * w;
   const int n_hblk = (h + HB - 1) / HB;
@@ -361,6 +367,7 @@ __global__ void __launch_bounds__(256) qk_prep_kernel(float* __restrict__ q, int
                                                       const float* __restrict__ rc,
                                                       const float* __restrict__ rs, int M, int N,
                                                       int heads) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -380,6 +387,7 @@ __global__ void __launch_bounds__(256) qk_prep_kernel(float* __restrict__ q, int
 }
 
 __global__ void split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, long long n4) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 v = x[i];
@@ -422,11 +430,11 @@ extern "C" int omt_layernorm(const float* x, int ldx, float* y, int ldy, const f
   const int nv = (C / 4 + 31) / 32;
   dim3 grid((M + 7) / 8), block(256);
   switch (nv) {
-    case 1: layernorm_kernel<1><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
-    case 2: layernorm_kernel<2><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
-    case 3: layernorm_kernel<3><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
-    case 4: layernorm_kernel<4><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
-    default: layernorm_kernel<8><<<grid, block, 0, st>>>(x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off); break;
+    case 1: OMT_CUDA(launch_k(layernorm_kernel<1>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
+    case 2: OMT_CUDA(launch_k(layernorm_kernel<2>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
+    case 3: OMT_CUDA(launch_k(layernorm_kernel<3>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
+    case 4: OMT_CUDA(launch_k(layernorm_kernel<4>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
+    default: OMT_CUDA(launch_k(layernorm_kernel<8>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
   }
   OMT_LAUNCH_CHECK();
   return OMT_OK;
@@ -448,11 +456,11 @@ extern "C" int omt_patchify_ln(const float* video, float* A, const float* ln_w, 
   dim3 grid((unsigned)((rows + 7) / 8)), block(256);
   const int nv = (K / 4 + 31) / 32;
   if (nv <= 2)
-    patchify_ln_kernel<2><<<grid, block, 0, st>>>(video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps);
+    OMT_CUDA(launch_k(patchify_ln_kernel<2>, grid, block, 0, st, video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   else if (nv <= 6)
-    patchify_ln_kernel<6><<<grid, block, 0, st>>>(video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps);
+    OMT_CUDA(launch_k(patchify_ln_kernel<6>, grid, block, 0, st, video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   else
-    patchify_ln_kernel<8><<<grid, block, 0, st>>>(video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps);
+    OMT_CUDA(launch_k(patchify_ln_kernel<8>, grid, block, 0, st, video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -469,7 +477,7 @@ extern "C" int omt_unpatchify(const float* P, float* video, int B, int Cin, int 
   if (total4 == 0) return OMT_OK;
   long long blocks = (total4 + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  unpatchify_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, video, total4, Cin, T, H, W, p, pt, first);
+  OMT_CUDA(launch_k(unpatchify_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, P, video, total4, Cin, T, H, W, p, pt, first));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -518,7 +526,7 @@ extern "C" int omt_peg_volume(const float* x, float* y, const float* w27, const 
   }
   const int threads = ((TT * HB * 8 + 31) / 32) * 32;
   dim3 grid(((T + TT - 1) / TT) * ((h + HB - 1) / HB), C / PEG_CC, B);
-  peg_tile_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS);
+  OMT_CUDA(launch_k(peg_tile_kernel, grid, dim3(threads), smem, (cudaStream_t)stream, x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -531,8 +539,8 @@ extern "C" int omt_qk_prep(float* q, int ldq, float* k, int ldk, const float* q_
   OMT_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "omt_qk_prep: cos/sin must both be given");
   OMT_REQUIRE(ldq % 2 == 0 && ldk % 2 == 0 && N > 0, "omt_qk_prep: bad leading dims");
   if (M == 0) return OMT_OK;
-  qk_prep_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, q_scale, k_scale, rope_cos,
-                                                                rope_sin, M, N, heads);
+  OMT_CUDA(launch_k(qk_prep_kernel, dim3((M + 7) / 8), dim3(256), 0, (cudaStream_t)stream, q, ldq, k, ldk, q_scale, k_scale,
+                    rope_cos, rope_sin, M, N, heads));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) pre_vq_kernel(const float* __restrict__ x
                                                      const float* __restrict__ Wt,
                                                      const float* __restrict__ b,
                                                      float* __restrict__ z, int M, int C, int l2) {
+  pdl_sync();
   extern __shared__ float4 wsm4[];   // [CD][C/4]
   const int C4 = C >> 2;
   for (int i = threadIdx.x; i < CD * C4; i += blockDim.x) wsm4[i] = reinterpret_cast<const float4*>(Wt)[i];
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict_
                                                         const float* __restrict__ e2, int M,
                                                         int n_codes, float* __restrict__ pd,
                                                         int* __restrict__ pi) {
+  pdl_sync();
   extern __shared__ float4 esm[];            // [per][2] float4 + e2[per]
   const int per = n_codes / VQ_SPLIT;
   const int k0 = blockIdx.y * per;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(256) vq_combine_kernel(const float* __restrict
                                                          const int* __restrict__ pi, int M,
                                                          int64_t* __restrict__ idx,
                                                          int32_t* __restrict__ counts) {
+  pdl_sync();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
   float best = pd[row];
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(128) post_vq_kernel(const int64_t* __restrict_
                                                       const float* __restrict__ Wt,
                                                       const float* __restrict__ b,
                                                       float* __restrict__ X, int M, int C) {
+  pdl_sync();
   __shared__ float rows[POSTVQ_ROWS][CD];
   const int r0 = blockIdx.x * POSTVQ_ROWS;
   for (int i = threadIdx.x; i < POSTVQ_ROWS * CD; i += blockDim.x) {
@@ -191,14 +195,14 @@ extern "C" int omt_pre_vq(const float* x, int ldx, const float* Wt, const float*
   const int cap = omt::sm_count() * 4;
   if (blocks > cap) blocks = cap;
   if (cd == 8) {
-    pre_vq_kernel<8><<<blocks, 256, smem, st>>>(x, ldx, Wt, b, z, M, C, l2);
+    OMT_CUDA(launch_k(pre_vq_kernel<8>, dim3(blocks), dim3(256), smem, st, x, ldx, Wt, b, z, M, C, l2));
   } else {
     static bool set16 = false;
     if (!set16) {
       OMT_CUDA(cudaFuncSetAttribute(pre_vq_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4));
       set16 = true;
     }
-    pre_vq_kernel<16><<<blocks, 256, smem, st>>>(x, ldx, Wt, b, z, M, C, l2);
+    OMT_CUDA(launch_k(pre_vq_kernel<16>, dim3(blocks), dim3(256), smem, st, x, ldx, Wt, b, z, M, C, l2));
   }
   OMT_LAUNCH_CHECK();
   return OMT_OK;
@@ -222,9 +226,9 @@ extern "C" int omt_vq_search(const float* z, const float* E, const float* e2, in
   float* pd = reinterpret_cast<float*>(workspace);
   int* pi = reinterpret_cast<int*>(pd + (size_t)VQ_SPLIT * M);
   dim3 grid((M + 255) / 256, VQ_SPLIT);
-  vq_search_kernel<<<grid, 256, smem, st>>>(z, E, e2, M, n_codes, pd, pi);
+  OMT_CUDA(launch_k(vq_search_kernel, grid, dim3(256), smem, st, z, E, e2, M, n_codes, pd, pi));
   OMT_LAUNCH_CHECK();
-  vq_combine_kernel<<<(M + 255) / 256, 256, 0, st>>>(pd, pi, M, idx, counts);
+  OMT_CUDA(launch_k(vq_combine_kernel, dim3((M + 255) / 256), dim3(256), 0, st, (const float*)pd, (const int*)pi, M, idx, counts));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -238,8 +242,8 @@ extern "C" int omt_post_vq(const int64_t* idx, const float* E, const float* zc, 
   OMT_REQUIRE(C % 4 == 0 && C <= 512, "omt_post_vq: C=%d unsupported", C);
   OMT_REQUIRE(cd == 8, "omt_post_vq: codebook_dim %d unsupported (8)", cd);
   if (M == 0) return OMT_OK;
-  post_vq_kernel<8><<<(M + POSTVQ_ROWS - 1) / POSTVQ_ROWS, 128, 0, (cudaStream_t)stream>>>(
-      idx, E, zc, z_st_from, zq_out, Wt, b, X, M, C);
+  OMT_CUDA(launch_k(post_vq_kernel<8>, dim3((M + POSTVQ_ROWS - 1) / POSTVQ_ROWS), dim3(128), 0, (cudaStream_t)stream,
+                    idx, E, zc, z_st_from, zq_out, Wt, b, X, M, C));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }

@@ -81,6 +81,7 @@ class Workspace:
 class Engine:
     def __init__(self, model, device: torch.device, math: Optional[str] = None):
         _cabi.load()
+        _cabi.set_option("pdl", int(os.environ.get("OMT_PDL", "0")))     # programmatic dependent launch between kernels
         self.device = device
         self.math_name = (math or default_math()).lower()
         if self.math_name not in MATH_MODES:
