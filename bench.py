@@ -130,7 +130,7 @@ def run_reference(args):
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     shape = (1,) + wl["shape"][1:]
     x = torch.rand(shape, generator=torch.Generator().manual_seed(1234)) - 0.5
-    cores = pick_cpu_threads(sd, x[:, :, :5] if x.ndim == 5 else x)
+    cores = pick_cpu_threads(sd, x)
     frames = shape[2] if len(shape) == 5 else 1
     for _ in range(args.warmup):
         cpu_oracle_run(sd, x)
@@ -318,7 +318,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
             xs = x_full[:1]
-            cores = pick_cpu_threads(sd, xs[:, :, :5] if xs.ndim == 5 else xs)
+            cores = pick_cpu_threads(sd, xs)
             cpu_oracle_run(sd, xs)                              # warm-up
             dt, idx_o, rec_o = cpu_oracle_run(sd, xs, reps=2)
             idx_g = m.encode(xs.to(dev), is_image)

@@ -179,12 +179,10 @@ class Engine:
     # ------------------------------------------------------------------ helpers
     @staticmethod
     def fuse_qkprep(M: int) -> bool:
-        """rope + l2norm + scale inside the QKV GEMM epilogue pays off once the epilogue is hidden behind the next
-        tile's main loop (many tiles per cluster); for small M the separate row-wise kernel is faster."""
-        mode = os.environ.get("OMT_FUSE_QKPREP", "auto")
-        if mode in ("0", "1"):
-            return mode == "1"
-        return M >= 16384
+        """rope + l2norm + scale ride in the QKV GEMM epilogue.  The choice must NOT depend on the batch size: the
+        fused epilogue and the stand-alone kernel round differently (x * (1/|x|) vs x / |x|, different reduction
+        trees), and a shard of a batch has to reproduce the full batch bit for bit (tests/test_gpu_fullsize.py)."""
+        return os.environ.get("OMT_FUSE_QKPREP", "1") != "0"
 
     def _workspace(self, M: int) -> Workspace:
         ws = self._ws.get(M)
