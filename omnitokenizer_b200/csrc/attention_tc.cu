@@ -9,7 +9,8 @@
 //   warp 1      TMEM alloc + single-thread MMA issue:
 //                 S_j  = Q K_j^T        A = Q (K-major), B = K_j (K-major)          -> TMEM S[j&1]
 //                 O_j  = P_j V_j        A = P_j (K-major, written by the softmax warps),
-//                                       B = V_j as loaded (MN-major descriptor)      -> TMEM O[j&1]
+//                                       B = V_j^T (K-major; V is transposed + split by the transform warps --
+//                                       an MN-major descriptor on V as loaded returned zeros on hardware) -> TMEM O[j&1]
 //               every product is 3 MMAs: lo.hi + hi.lo + hi.hi (tf32 operands, fp32 accumulate)
 //   warps 2-5   transform: split Q, K_j, V_j into tf32 hi (in place) / lo in shared memory
 //   warps 6-9   softmax: one thread per query row; S_j from TMEM, online max / sum in fp32 (exp2),
@@ -33,9 +34,8 @@ constexpr int OFF_VH = OFF_KL + K_BYTES, OFF_VL = OFF_VH + K_BYTES, OFF_PH = OFF
 constexpr int OFF_VR = OFF_PL + P_BYTES, OFF_KR = OFF_VR + K_BYTES;   // TMA landing buffers (raw fp32)
 constexpr int SMEM = OFF_KR + K_BYTES + 1024;        // 224 KiB + alignment slack
 constexpr int THREADS = 320;
-// tf32 x tf32 -> f32, M=128, N=64; bit 16 = B is MN-major (used for V)
+// tf32 x tf32 -> f32, M=128, N=64, both operands K-major
 constexpr uint32_t IDESC_KK = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-constexpr uint32_t IDESC_KMN = IDESC_KK | (1u << 16);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -84,11 +84,6 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
-}
-// MN-major SW128 operand: 32-element (128 B) chunks along MN repeat every `lbo` bytes, 8-row K groups every 1024 B
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo) {
-  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);

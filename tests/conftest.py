@@ -19,3 +19,20 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _reset_kernel_options(request):
+    """GPU tests flip process-wide kernel selectors (omt_set_option); restore the defaults afterwards."""
+    yield
+    if request.node.get_closest_marker("gpu") is None:
+        return
+    try:
+        from omnitokenizer_b200 import _cabi
+        if _cabi._lib is not None:
+            _cabi.set_option("tc_kernel", 2)
+            _cabi.set_option("tc_block_n", 128)
+            _cabi.set_option("attn_kernel", 3)
+            _cabi.set_option("attn_debug", 0)
+    except Exception:
+        pass
