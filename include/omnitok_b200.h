@@ -88,7 +88,8 @@ int omt_layernorm(const float* x, int ldx, float* y, int ldy, const float* w, co
 
 /* Patch gather + LayerNorm (omnitokenizer.py:806-808 / :814-817: Rearrange + nn.LayerNorm).
  * video (B, Cin, T, H, W) fp32 contiguous.  first=1: frame 0, rows (b,h,w), features (c,p1,p2);
- * first=0: frames 1.., rows (b,t,h,w), features (c,pt,p1,p2).  A is [rows, K] dense. */
+ * first=0: frames 1.., rows (b,t,h,w), features (c,pt,p1,p2).  A is [rows, K] dense.
+ * ln_w == ln_b == NULL: plain patch gather (im2col of the strided Conv3d of patch_embed='cnn', omnitokenizer.py:823-838). */
 int omt_patchify_ln(const float* video, float* A, const float* ln_w, const float* ln_b,
                     int B, int Cin, int T, int H, int W, int p, int pt, int first, float eps,
                     omt_stream_t stream);

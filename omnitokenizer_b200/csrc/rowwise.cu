@@ -140,6 +140,15 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  float* ar = A + (size_t)row * K;
+  if (lw == nullptr) {        // plain im2col (patch_embed='cnn': the strided Conv3d is a GEMM on raw patch vectors)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int f = (i * 32 + lane) * 4;
+      if (f < K) *reinterpret_cast<float4*>(ar + f) = v[i];
+    }
+    return;
+  }
   const float mean = warp_sum(s) / (float)K;
   float q = 0.f;
 #pragma unroll
@@ -151,7 +160,6 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
     }
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + eps);
-  float* ar = A + (size_t)row * K;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int f = (i * 32 + lane) * 4;
@@ -444,7 +452,7 @@ extern "C" int omt_patchify_ln(const float* video, float* A, const float* ln_w, 
                                int Cin, int T, int H, int W, int p, int pt, int first, float eps,
                                omt_stream_t stream) {
   OMT_ENTER();
-  OMT_REQUIRE(video && A && ln_w && ln_b, "omt_patchify_ln: null pointer");
+  OMT_REQUIRE(video && A && ((ln_w == nullptr) == (ln_b == nullptr)), "omt_patchify_ln: null pointer");
   OMT_REQUIRE(p % 4 == 0 && H % p == 0 && W % p == 0, "omt_patchify_ln: patch %d must be a multiple of 4 dividing %dx%d", p, H, W);
   OMT_REQUIRE(first || (T > 1 && (T - 1) % pt == 0), "omt_patchify_ln: (T-1) %% pt != 0");
   const int PT = first ? 1 : pt;

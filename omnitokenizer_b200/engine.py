@@ -164,10 +164,34 @@ class Engine:
         self.dec_spatial = transformer("decoder.dec_spatial_transformer", a.dec_block)
 
         self.pe = {}
-        for key, pre in (("first", "encoder.to_patch_emb_first_frame"), ("rest", "encoder.to_patch_emb")):
-            self.pe[key] = dict(ln1_g=f32(sd[pre + ".1.weight"]), ln1_b=f32(sd[pre + ".1.bias"]), lin=lin(pre + ".2"),
-                                ln2_g=f32(sd[pre + ".3.weight"]), ln2_b=f32(sd[pre + ".3.bias"]))
-        self.px = {"first": lin("decoder.to_pixels_first_frame.0"), "rest": lin("decoder.to_pixels.0")}
+        self.cnn = getattr(a, "patch_embed", "linear") == "cnn"
+        if self.cnn:
+            # patch_embed='cnn' (omnitokenizer.py:823-838, 1019-1035): a Conv3d with kernel == stride is a GEMM over
+            # the same (c, pt, p1, p2) patch vectors as the linear variant, and eval-mode (Sync)BatchNorm is a
+            # per-channel affine -> both fold into ONE packed weight/bias; no LayerNorms in this variant.
+            def bn_affine(pre):
+                g, b = sd[pre + ".weight"].float(), sd[pre + ".bias"].float()
+                rm, rv = sd[pre + ".running_mean"].float(), sd[pre + ".running_var"].float()
+                s_ = g / torch.sqrt(rv + 1e-5)
+                return s_, b - rm * s_
+            for key, pre in (("first", "encoder.to_patch_emb_first_frame"), ("rest", "encoder.to_patch_emb")):
+                w = sd[pre + ".0.weight"].float().reshape(self.C, -1)                 # (dim, c*pt*p*p)
+                s_, t_ = bn_affine(pre + ".1")
+                self.pe[key] = dict(ln1_g=None, ln1_b=None, ln2_g=None, ln2_b=None,
+                                    lin=PackedLinear(w * s_[:, None], sd[pre + ".0.bias"].float() * s_ + t_, dev, m))
+            self.px = {}
+            for key, pre in (("first", "decoder.to_pixels_first_frame"), ("rest", "decoder.to_pixels")):
+                wt = sd[pre + ".1.weight"].float()                                    # (dim, channels, pt, p, p)
+                per_c = wt[0, 0].numel()
+                s_, t_ = bn_affine(pre + ".2")
+                w = wt.reshape(self.C, -1).t() * s_.repeat_interleave(per_c)[:, None]  # (channels*pt*p*p, dim)
+                bias = (sd[pre + ".1.bias"].float() * s_ + t_).repeat_interleave(per_c)
+                self.px[key] = PackedLinear(w.contiguous(), bias, dev, m)
+        else:
+            for key, pre in (("first", "encoder.to_patch_emb_first_frame"), ("rest", "encoder.to_patch_emb")):
+                self.pe[key] = dict(ln1_g=f32(sd[pre + ".1.weight"]), ln1_b=f32(sd[pre + ".1.bias"]), lin=lin(pre + ".2"),
+                                    ln2_g=f32(sd[pre + ".3.weight"]), ln2_b=f32(sd[pre + ".3.bias"]))
+            self.px = {"first": lin("decoder.to_pixels_first_frame.0"), "rest": lin("decoder.to_pixels.0")}
         self.pre_w, self.pre_b = f32(sd["pre_vq_conv.1.weight"]), f32(sd["pre_vq_conv.1.bias"])
         self.post_w, self.post_b = f32(sd["post_vq_conv.1.weight"]), f32(sd["post_vq_conv.1.bias"])
         E = sd["codebook.embeddings"].detach().float()
@@ -305,7 +329,8 @@ class Engine:
         _cabi.call("omt_patchify_ln", x, ws.P, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p, self.pt, 1, 1e-5)
         cmap = (N, Tp * N, 0)
         self._linear(ws.P, k1, pe["lin"], ws.X, C, B * N, c_map=cmap)
-        self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], B * N, seg=cmap)
+        if not self.cnn:
+            self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], B * N, seg=cmap)
         if Tp > 1:
             pe = self.pe["rest"]
             k2 = k1 * self.pt
@@ -314,7 +339,8 @@ class Engine:
                        1e-5)
             cmap = ((Tp - 1) * N, Tp * N, N)
             self._linear(ws.P, k2, pe["lin"], ws.X, C, rows, c_map=cmap)
-            self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], rows, seg=cmap)
+            if not self.cnn:
+                self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], rows, seg=cmap)
         self._transformer(self.enc_spatial, ws, B, Tp, h, w, temporal=False)
         self._transformer(self.enc_temporal, ws, B, Tp, h, w, temporal=True)
         cd = self.pre_w.shape[0]

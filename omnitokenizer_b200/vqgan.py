@@ -118,21 +118,33 @@ def _pair(v):
     return v if isinstance(v, tuple) else (v, v)
 
 
+def _check_patch_embed(a):
+    if a.patch_embed not in ("linear", "cnn"):
+        raise NotImplementedError(f"patch_embed={a.patch_embed!r}: the reference itself raises for anything but linear / cnn")
+    if a.patch_embed == "cnn" and getattr(a, "norm_type", "batch") != "batch":
+        # Normalize(image_channels=3, 'group') is GroupNorm(32 groups, 3 channels): the reference cannot even construct it
+        raise NotImplementedError("patch_embed='cnn' needs --norm_type batch (GroupNorm(32, 3) is invalid in the reference too)")
+
+
 class OmniTokenizer_Encoder(nn.Module):   # omnitokenizer.py:772-868
     def __init__(self, a):
         super().__init__()
-        if a.patch_embed != "linear":
-            raise NotImplementedError("patch_embed='cnn' (omnitokenizer.py:823-838) is not implemented; every shipped "
-                                      "script uses 'linear'")
+        _check_patch_embed(a)
         self.image_size = _pair(a.resolution)
         self.patch_size = _pair(a.patch_size)
         self.temporal_patch_size = a.temporal_patch_size
         self.block = a.enc_block
         k = a.image_channels * a.patch_size * a.patch_size
         dim = a.embedding_dim
-        self.to_patch_emb_first_frame = nn.Sequential(_Slot(), nn.LayerNorm(k), nn.Linear(k, dim), nn.LayerNorm(dim))
-        self.to_patch_emb = nn.Sequential(_Slot(), nn.LayerNorm(k * a.temporal_patch_size),
-                                          nn.Linear(k * a.temporal_patch_size, dim), nn.LayerNorm(dim))
+        p, pt = a.patch_size, a.temporal_patch_size
+        if a.patch_embed == "cnn":      # omnitokenizer.py:823-838: Conv3d + Normalize('batch' = SyncBatchNorm) + Rearrange
+            self.to_patch_emb_first_frame = nn.Sequential(nn.Conv3d(a.image_channels, dim, (1, p, p), stride=(1, p, p)),
+                                                          nn.BatchNorm3d(dim), _Slot())
+            self.to_patch_emb = nn.Sequential(nn.Conv3d(a.image_channels, dim, (pt, p, p), stride=(pt, p, p)),
+                                              nn.BatchNorm3d(dim), _Slot())
+        else:
+            self.to_patch_emb_first_frame = nn.Sequential(_Slot(), nn.LayerNorm(k), nn.Linear(k, dim), nn.LayerNorm(dim))
+            self.to_patch_emb = nn.Sequential(_Slot(), nn.LayerNorm(k * pt), nn.Linear(k * pt, dim), nn.LayerNorm(dim))
         kw = dict(dim=dim, dim_head=a.dim_head, heads=a.heads, ff_mult=a.ff_mult, window_size=a.twod_window_size)
         self.enc_spatial_transformer = _Transformer(block=a.enc_block, spatial_pos=a.spatial_pos, **kw)
         # temporal transformers are built without spatial_pos -> default "rel" -> dead bias-MLP keys
@@ -150,8 +162,16 @@ class OmniTokenizer_Decoder(nn.Module):   # omnitokenizer.py:950-1035
         kw = dict(dim=dim, dim_head=a.dim_head, heads=a.heads, ff_mult=a.ff_mult, window_size=a.twod_window_size)
         self.dec_spatial_transformer = _Transformer(block=a.dec_block, spatial_pos=a.spatial_pos, **kw)
         self.dec_temporal_transformer = _Transformer(block="t" * a.temporal_depth, spatial_pos="rel", **kw)
-        self.to_pixels_first_frame = nn.Sequential(nn.Linear(dim, k), _Slot())
-        self.to_pixels = nn.Sequential(nn.Linear(dim, k * a.temporal_patch_size), _Slot())
+        _check_patch_embed(a)
+        p, pt = a.patch_size, a.temporal_patch_size
+        if a.patch_embed == "cnn":      # omnitokenizer.py:1019-1035: Rearrange + ConvTranspose3d + Normalize(channels)
+            self.to_pixels_first_frame = nn.Sequential(_Slot(), nn.ConvTranspose3d(dim, a.image_channels, (1, p, p),
+                                                                                  stride=(1, p, p)), nn.BatchNorm3d(a.image_channels))
+            self.to_pixels = nn.Sequential(_Slot(), nn.ConvTranspose3d(dim, a.image_channels, (pt, p, p), stride=(pt, p, p)),
+                                           nn.BatchNorm3d(a.image_channels))
+        else:
+            self.to_pixels_first_frame = nn.Sequential(nn.Linear(dim, k), _Slot())
+            self.to_pixels = nn.Sequential(nn.Linear(dim, k * pt), _Slot())
 
 
 class Codebook(nn.Module):                # modules/codebook.py:11-28
@@ -300,6 +320,12 @@ class OmniTokenizer_VQGAN(nn.Module):
             z = mean + torch.exp(0.5 * logvar) * noise
             return z.squeeze(2) if is_image else z.contiguous()
 
+    def _check_cnn_grid(self, h, w):
+        # the cnn decoder's Rearrange pins h to image_size // patch_size (omnitokenizer.py:1021): other grids raise there
+        if self.args.patch_embed == "cnn" and h != self.resolution // self.patch_size:
+            raise ValueError(f"patch_embed='cnn' decodes only the configured resolution ({self.resolution}): "
+                             f"token grid {h}x{w} != {self.resolution // self.patch_size}")
+
     @torch.no_grad()
     def decode(self, encodings, is_image):
         """omnitokenizer.py:268-317 (index / flat-index / VAE 4-D 'b c h w' / 5-D 'b t h w c' conventions)."""
@@ -317,6 +343,7 @@ class OmniTokenizer_VQGAN(nn.Module):
                     raise ValueError("image indices must be (B, h*w) or (B, 1, h, w)")
                 else:
                     B, Tp, h, w = enc.shape
+                self._check_cnn_grid(h, w)
                 idx = enc.reshape(-1).to(device=self.device, dtype=torch.int64)
                 video = eng.decode((B, Tp, h, w), idx=idx)
             else:
@@ -335,6 +362,7 @@ class OmniTokenizer_VQGAN(nn.Module):
                     else:
                         B, Tp, h, w, c = z.shape
                         zc = z.reshape(B * Tp * h * w, c)
+                self._check_cnn_grid(h, w)
                 video = eng.decode((B, Tp, h, w), zc=zc)
             return video.squeeze(2) if is_image else video
 

@@ -24,6 +24,8 @@ CASES = [
     ("img256_cfg1", [], (1, 3, 256, 256), 0, 1237),
     ("vae_vid5x64", ["--use_vae"], (1, 3, 5, 64, 64), 2, 1238),
     ("vae_img64", ["--use_vae"], (2, 3, 64, 64), 2, 1239),
+    # patch_embed='cnn' (Conv3d + eval BatchNorm); its decoder only handles the configured resolution
+    ("cnn_vid5x64", ["--patch_embed", "cnn", "--resolution", "64"], (1, 3, 5, 64, 64), 4, 1240),
 ]
 
 
@@ -50,7 +52,8 @@ def main():
         m.codebook._need_init = False
         x = W.synthetic_input(shape, xseed)
         is_image = x.ndim == 4
-        fx = {"name": name, "use_vae": cfg.use_vae, "shape": shape, "wseed": wseed, "xseed": xseed,
+        fx = {"name": name, "use_vae": cfg.use_vae, "patch_embed": cfg.patch_embed, "resolution": cfg.resolution,
+              "shape": shape, "wseed": wseed, "xseed": xseed,
               "fingerprint": W.fingerprint(sd), "x_sum64": float(x.double().sum()),
               "torch": torch.__version__}
         taps = {}

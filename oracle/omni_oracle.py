@@ -62,6 +62,7 @@ class Config:
     codebook_dim: int = 8
     l2_code: bool = True
     use_vae: bool = False
+    patch_embed: str = "linear"      # 'linear' (every shipped script) | 'cnn' (Conv3d + eval-mode BatchNorm)
 
     @property
     def ff_inner(self) -> int:  # modules/attention.py:161
@@ -129,6 +130,8 @@ def patch_embed(sd: SD, cfg: Config, video: Tensor) -> Tensor:
     """omnitokenizer.py:919-947 + 806-822: LN -> Linear -> LN per patch; returns X (B,T',N,C)."""
     p, pt = cfg.patch_size, cfg.temporal_patch_size
     assert (video.shape[2] - 1) % pt == 0, "number of frames minus one must be divisible by temporal patch size"
+    if cfg.patch_embed == "cnn":
+        return patch_embed_cnn(sd, cfg, video)
     first, rest = patchify(video, p, pt)
 
     def emb(x, pre):
@@ -143,8 +146,44 @@ def patch_embed(sd: SD, cfg: Config, video: Tensor) -> Tensor:
     return tok.reshape(B, T, h * w, C)
 
 
+def _bn_eval(x: Tensor, sd: SD, pre: str) -> Tensor:
+    """base.py:272-277 Normalize(norm_type='batch') = SyncBatchNorm; in eval it is the running-stats affine."""
+    return F.batch_norm(x, sd[pre + ".running_mean"], sd[pre + ".running_var"], sd[pre + ".weight"], sd[pre + ".bias"],
+                        False, 0.0, 1e-5)
+
+
+def patch_embed_cnn(sd: SD, cfg: Config, video: Tensor) -> Tensor:
+    """omnitokenizer.py:823-838: strided Conv3d (kernel = stride = (1|pt, p, p)) + Normalize, no LayerNorms."""
+    p, pt = cfg.patch_size, cfg.temporal_patch_size
+    pre = "encoder.to_patch_emb_first_frame"
+    tok = _bn_eval(F.conv3d(video[:, :, :1], sd[pre + ".0.weight"], sd[pre + ".0.bias"], stride=(1, p, p)), sd, pre + ".1")
+    if video.shape[2] > 1:
+        pre = "encoder.to_patch_emb"
+        r = _bn_eval(F.conv3d(video[:, :, 1:], sd[pre + ".0.weight"], sd[pre + ".0.bias"], stride=(pt, p, p)), sd, pre + ".1")
+        tok = torch.cat([tok, r], dim=2)
+    B, C, T, h, w = tok.shape
+    return tok.permute(0, 2, 3, 4, 1).reshape(B, T, h * w, C)
+
+
+def to_pixels_cnn(sd: SD, cfg: Config, X: Tensor, hw: Tuple[int, int]) -> Tensor:
+    """omnitokenizer.py:1019-1035: ConvTranspose3d (kernel = stride) + Normalize(image_channel)."""
+    B, T, N, C = X.shape
+    h, w = hw
+    p, pt = cfg.patch_size, cfg.temporal_patch_size
+    vol = X.reshape(B, T, h, w, C).permute(0, 4, 1, 2, 3)
+    pre = "decoder.to_pixels_first_frame"
+    out = _bn_eval(F.conv_transpose3d(vol[:, :, :1], sd[pre + ".1.weight"], sd[pre + ".1.bias"], stride=(1, p, p)), sd, pre + ".2")
+    if T > 1:
+        pre = "decoder.to_pixels"
+        r = _bn_eval(F.conv_transpose3d(vol[:, :, 1:], sd[pre + ".1.weight"], sd[pre + ".1.bias"], stride=(pt, p, p)), sd, pre + ".2")
+        out = torch.cat([out, r], dim=2)
+    return out
+
+
 def to_pixels(sd: SD, cfg: Config, X: Tensor, hw: Tuple[int, int]) -> Tensor:
     """omnitokenizer.py:1089-1094."""
+    if cfg.patch_embed == "cnn":
+        return to_pixels_cnn(sd, cfg, X, hw)
     B, T, N, C = X.shape
     h, w = hw
     tok = X.reshape(B, T, h, w, C)

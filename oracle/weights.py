@@ -41,10 +41,24 @@ def make_state_dict(cfg: Config, seed: int = 0) -> Dict[str, torch.Tensor]:
     p, pt, ch = cfg.patch_size, cfg.temporal_patch_size, cfg.image_channels
     k1, k2 = ch * p * p, ch * p * p * pt
 
-    for pre, k in (("encoder.to_patch_emb_first_frame", k1), ("encoder.to_patch_emb", k2)):
-        ln(pre + ".1", k)
-        linear(pre + ".2", C, k)
-        ln(pre + ".3", C)
+    def bn(name, dim):
+        sd[name + ".weight"] = uni((dim,), 0.5, 1.5)
+        sd[name + ".bias"] = uni((dim,), -0.1, 0.1)
+        sd[name + ".running_mean"] = uni((dim,), -0.2, 0.2)
+        sd[name + ".running_var"] = uni((dim,), 0.5, 1.5)
+        sd[name + ".num_batches_tracked"] = torch.tensor(1000, dtype=torch.int64)
+
+    cnn = cfg.patch_embed == "cnn"
+    for pre, k, PT in (("encoder.to_patch_emb_first_frame", k1, 1), ("encoder.to_patch_emb", k2, pt)):
+        if cnn:       # omnitokenizer.py:823-838
+            b = 1.0 / math.sqrt(k)
+            sd[pre + ".0.weight"] = uni((C, ch, PT, p, p), -b, b)
+            sd[pre + ".0.bias"] = uni((C,), -b, b)
+            bn(pre + ".1", C)
+        else:
+            ln(pre + ".1", k)
+            linear(pre + ".2", C, k)
+            ln(pre + ".3", C)
 
     def t_layer(lp, temporal):
         b = 1.0 / math.sqrt(27)
@@ -98,8 +112,15 @@ def make_state_dict(cfg: Config, seed: int = 0) -> Dict[str, torch.Tensor]:
     tr("encoder.enc_temporal_transformer", "t" * cfg.temporal_depth, True)
     tr("decoder.dec_spatial_transformer", cfg.dec_block, False)
     tr("decoder.dec_temporal_transformer", "t" * cfg.temporal_depth, True)
-    linear("decoder.to_pixels_first_frame.0", k1, C)
-    linear("decoder.to_pixels.0", k2, C)
+    if cnn:           # omnitokenizer.py:1019-1035: ConvTranspose3d weight is (in=dim, out=channels, kt, kh, kw)
+        for pre, PT in (("decoder.to_pixels_first_frame", 1), ("decoder.to_pixels", pt)):
+            b = 1.0 / math.sqrt(C)
+            sd[pre + ".1.weight"] = uni((C, ch, PT, p, p), -b, b)
+            sd[pre + ".1.bias"] = uni((ch,), -b, b)
+            bn(pre + ".2", ch)
+    else:
+        linear("decoder.to_pixels_first_frame.0", k1, C)
+        linear("decoder.to_pixels.0", k2, C)
     # codebook ~ N(0,1)-ish (Irwin-Hall of 12 uniforms: exact adds, no transcendental)
     E = torch.rand((cfg.n_codes, cfg.codebook_dim, 12), generator=g).sum(-1) - 6.0
     sd["codebook.embeddings"] = E

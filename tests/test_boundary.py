@@ -21,10 +21,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_state_dict_layout_matches_reference_checkpoint():
     """Same key names / shapes / dtypes as the reference for everything on the hot path
     (oracle/weights.py reproduces SURVEY.md Appendix B and is itself checked against the reference)."""
-    for extra in ([], ["--use_vae"]):
+    for extra in ([], ["--use_vae"], ["--patch_embed", "cnn"]):
         a = ob.canonical_args(extra)
         m = ob.OmniTokenizer_VQGAN(a)
-        sd = W.make_state_dict(oo.Config(use_vae=bool(extra)), 0)
+        sd = W.make_state_dict(oo.Config(use_vae="--use_vae" in extra, patch_embed="cnn" if "cnn" in extra else "linear"), 0)
         mine = m.state_dict()
         assert set(mine) == set(sd)
         for k in sd:

@@ -19,7 +19,7 @@ def _math_modes():
 
 
 @pytest.mark.parametrize("math", _math_modes())
-@pytest.mark.parametrize("name", ["img64", "vid5x64", "vid9x128_b2", "img256_cfg1"])
+@pytest.mark.parametrize("name", ["img64", "vid5x64", "vid9x128_b2", "img256_cfg1", "cnn_vid5x64"])
 def test_vq_encode_decode_matches_golden(cuda, name, math):
     fx = load_golden(name)
     cfg, sd, x = golden_setup(fx)

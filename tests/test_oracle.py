@@ -8,7 +8,7 @@ from oracle import ref_loader as rl
 from oracle import weights as W
 from tests.util import GOLDEN_CASES, check_sub, golden_setup, load_golden
 
-FAST = ["img64", "vid5x64", "vae_vid5x64", "vae_img64"]
+FAST = ["img64", "vid5x64", "vae_vid5x64", "vae_img64", "cnn_vid5x64"]
 
 
 @pytest.mark.parametrize("name", FAST + ["vid9x128_b2", "img256_cfg1"])

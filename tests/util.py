@@ -8,7 +8,7 @@ from oracle import omni_oracle as oo
 from oracle import weights as W
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["img64", "vid5x64", "vid9x128_b2", "img256_cfg1", "vae_vid5x64", "vae_img64"]
+GOLDEN_CASES = ["img64", "vid5x64", "vid9x128_b2", "img256_cfg1", "vae_vid5x64", "vae_img64", "cnn_vid5x64"]
 
 
 def load_golden(name):
@@ -17,7 +17,8 @@ def load_golden(name):
 
 def golden_setup(fx):
     """Rebuild (cfg, state_dict, input) of a fixture and prove the recipe reproduced the same bits."""
-    cfg = oo.Config(use_vae=bool(fx["use_vae"]))
+    cfg = oo.Config(use_vae=bool(fx["use_vae"]), patch_embed=fx.get("patch_embed", "linear"),
+                    resolution=fx.get("resolution", 256))
     sd = W.make_state_dict(cfg, fx["wseed"])
     assert W.fingerprint(sd) == fx["fingerprint"], "synthetic checkpoint differs from the one the golden run used"
     x = W.synthetic_input(fx["shape"], fx["xseed"])
@@ -47,6 +48,10 @@ def namespace_from_cfg(cfg: oo.Config, **over):
     extra = []
     if cfg.use_vae:
         extra.append("--use_vae")
+    if cfg.patch_embed != "linear":
+        extra += ["--patch_embed", cfg.patch_embed]
+    if cfg.resolution != 256:
+        extra += ["--resolution", str(cfg.resolution)]
     a = ob.canonical_args(extra)
     for k, v in over.items():
         setattr(a, k, v)
