@@ -100,6 +100,16 @@ __device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, u
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
@@ -225,8 +235,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA, one thread) =================
-    if (leader && lane == 0) {
+    // ================= MMA issuer (leader CTA; the warp stays converged, one elected lane issues) =================
+    if (leader) {
       uint32_t it = 0, tcount = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
         const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
@@ -239,19 +249,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(&w_full[s], ph);
           mbar_wait(&ready[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_ptr(s));
-          const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + A_BYTES);
-          const uint64_t d_whi = make_desc(sa + 2 * A_BYTES), d_wlo = make_desc(sa + 2 * A_BYTES + W_BYTES);
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(stage_ptr(s));
+            const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + A_BYTES);
+            const uint64_t d_whi = make_desc(sa + 2 * A_BYTES), d_wlo = make_desc(sa + 2 * A_BYTES + W_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            mma_tf32_pair(d_tmem, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
-            mma_tf32_pair(d_tmem, d_ahi + adv, d_wlo + adv, IDESC, 1);
-            mma_tf32_pair(d_tmem, d_ahi + adv, d_whi + adv, IDESC, 1);
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
+              mma_tf32_pair(d_tmem, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
+              mma_tf32_pair(d_tmem, d_ahi + adv, d_wlo + adv, IDESC, 1);
+              mma_tf32_pair(d_tmem, d_ahi + adv, d_whi + adv, IDESC, 1);
+            }
+            tc_commit_pair(&empty[s]);
+            if (kb == num_kb - 1) tc_commit_pair(&tmem_full[acc]);
           }
-          tc_commit_pair(&empty[s]);
+          __syncwarp();
         }
-        tc_commit_pair(&tmem_full[acc]);
       }
     }
     __syncwarp();
