@@ -14,97 +14,19 @@
 //   warps 2..5  : hi/lo transform of the A stage in smem (generic proxy -> fence.proxy.async),
 //                 then the epilogue: tcgen05.ld 32x32b -> smem transpose -> coalesced 16 B stores.
 #include "omt_common.cuh"
+#include "tc_ptx.cuh"
 #include <cuda.h>
 #include <string.h>
 
 namespace omt {
 
-
 namespace tc {
+using namespace omt::ptx;
 
 constexpr int BM = 128;
 constexpr int BK = 32;                      // fp32 elements per k-block (128 bytes)
 constexpr int A_BYTES = BM * BK * 4;        // 16 KiB
 constexpr int SMEM_BUDGET = 216 * 1024;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  const long long t0 = clock64();
-  for (uint32_t it = 0;; ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t"
-        "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (ok) break;
-    // watchdog: a protocol bug must trap, not hang the GPU box
-    if ((it & 0x3ff) == 0x3ff && clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// K-major, SWIZZLE_128B canonical tile: rows 128 B apart, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fff);          // start address
-  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
-  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ float tf32_rn(float x) {
-  // round-to-nearest (ties away) on the 13 dropped mantissa bits == cvt.rna.tf32.f32 for finite x,
-  // but 2 integer ops instead of the ~7-instruction sequence ptxas emits for the cvt
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
 
 template <int BN, bool SPLIT>
 struct Cfg {
@@ -193,21 +115,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t sa = smem_u32(stage_ptr(s));
         if (SPLIT) {
-          const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + A_BYTES);
-          const uint64_t d_whi = make_desc(sa + 2 * A_BYTES), d_wlo = make_desc(sa + 2 * A_BYTES + C::W_BYTES);
+          const uint64_t d_ahi = desc_kmajor(sa), d_alo = desc_kmajor(sa + A_BYTES);
+          const uint64_t d_whi = desc_kmajor(sa + 2 * A_BYTES), d_wlo = desc_kmajor(sa + 2 * A_BYTES + C::W_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 32 bytes per k-step inside the swizzle row
-            mma_tf32_ss(tmem_base, d_alo + adv, d_whi + adv, C::IDESC, (kb | k) != 0);
-            mma_tf32_ss(tmem_base, d_ahi + adv, d_wlo + adv, C::IDESC, 1);
-            mma_tf32_ss(tmem_base, d_ahi + adv, d_whi + adv, C::IDESC, 1);
+            mma_tf32(tmem_base, d_alo + adv, d_whi + adv, C::IDESC, (kb | k) != 0);
+            mma_tf32(tmem_base, d_ahi + adv, d_wlo + adv, C::IDESC, 1);
+            mma_tf32(tmem_base, d_ahi + adv, d_whi + adv, C::IDESC, 1);
           }
         } else {
-          const uint64_t d_a = make_desc(sa), d_w = make_desc(sa + A_BYTES);
+          const uint64_t d_a = desc_kmajor(sa), d_w = desc_kmajor(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            mma_tf32_ss(tmem_base, d_a + adv, d_w + adv, C::IDESC, (kb | k) != 0);
+            mma_tf32(tmem_base, d_a + adv, d_w + adv, C::IDESC, (kb | k) != 0);
           }
         }
         tc_commit(&empty_bar[s]);     // frees the smem stage once these MMAs retire
