@@ -258,7 +258,7 @@ def main():
     # their own streams (separate DMA engines) while step i computes; all copies are inside the timed region
     # (one event pair around the K steps, the end event waits for the last D2H).
     out_host = [torch.empty((e - s,) + shape[1:], dtype=torch.float32).pin_memory() for _ in range(2)]
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, args.steps)
     main = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     xd = [torch.empty_like(x_dev) for _ in range(2)]
@@ -291,6 +291,16 @@ def main():
             main.wait_event(ev_out[sl])                      # the end event below is ordered after the last D2H
 
     barrier()
+    # link speed of THIS box (untimed, explains e2e - value: boxes differ by several x in host copy bandwidth)
+    c_a, c_b, c_c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    c_a.record(main)
+    xd[0].copy_(x_host, non_blocking=True)
+    c_b.record(main)
+    out_host[0].copy_(xd[0], non_blocking=True)
+    c_c.record(main)
+    barrier()
+    link = {"h2d_GBps": round(x_host.numel() * 4 / c_a.elapsed_time(c_b) / 1e6, 1) if x_host.numel() else None,
+            "d2h_GBps": round(x_host.numel() * 4 / c_b.elapsed_time(c_c) / 1e6, 1) if x_host.numel() else None}
     e2e_run(2)                                               # warm the pipeline (untimed)
     barrier()
     flush.add_(1.0)
@@ -346,7 +356,8 @@ def main():
                        "l2": "256 MiB flush between timed steps (untimed); activations >> L2"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": out_host[0].numel() * 4, "ms_per_step": round(t2_ms / e2e_steps, 3),
-                    "steps": e2e_steps, "pipeline": "H2D / compute / D2H of consecutive steps overlap on 3 streams"},
+                    "steps": e2e_steps, "pipeline": "H2D / compute / D2H of consecutive steps overlap on 3 streams",
+                    "host_link": link},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
         if not args.no_cpu_baseline and world == 1:

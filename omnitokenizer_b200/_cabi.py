@@ -102,6 +102,10 @@ def call(name: str, *args):
         raise RuntimeError(f"{name} failed ({rc}): {lib.omt_last_error().decode()}")
 
 
+# process-wide kernel selectors and their library defaults (omt_set_option); tests restore these after flipping them
+DEFAULT_OPTIONS = {"tc_kernel": 2, "tc_block_n": 128, "attn_kernel": 3, "attn_debug": 0, "peg_kernel": 3}
+
+
 def set_option(name: str, value: int):
     lib = load()
     rc = lib.omt_set_option(name.encode(), int(value))

@@ -15,6 +15,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int g_peg_kernel = 3;   // omt_set_option("peg_kernel", 3|4): 3 = peg_tile_kernel, 4 = peg_tile4_kernel (cp.async + FFMA2)
 int g_pdl = 0;   // measured on B200: PDL made the step 2-4 % slower (dependent CTAs hold SM resources during the tail), so it is opt-in
 static int g_dev_ok[64];   // 0 unknown, 1 ok, -1 bad
 static int g_sms[64];
@@ -351,6 +352,145 @@ __global__ void __launch_bounds__(256) peg_tile_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// PEG, tiled form v4: same tile geometry and the SAME fma order as peg_tile_kernel (bit-identical output), with
+// the instruction count cut ~3x (the v3 kernel is issue-bound: ncu 67 M warp instructions, 102 per output):
+//   * halo gather by cp.async (16 B, zero-fill where the reference pads): no register staging, no position-map
+//     pass; one warp walks one halo row at a time so the only divisions are per row (warp-uniform) and the
+//     temporal  f -> (f % T, f / T)  split is a multiply-shift on the in-row offset;
+//   * the 3x3x3 register window rotates by renaming (w loop unrolled by 3) instead of 36 MOVs per output;
+//   * packed fma.rn.f32x2 (FFMA2): one instruction per channel PAIR and tap.
+// Requires T <= 64, w <= 254 (multiply-shift range) and 16-byte aligned x; the host falls back to v3 otherwise.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<uint64_t*>(&d))
+      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)),
+        "l"(*reinterpret_cast<const uint64_t*>(&c)));
+  return d;
+}
+
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+// One output position of a strip.  R = window rotation: tap kw of window row r9 lives in slot (kw + R) % 3;
+// the new halo column is read at a[r9] + R * 64 bytes (a[] points at the trip's first new column).
+template <int R>
+__device__ __forceinline__ float2 peg_step(float2 (&win)[9][3], const float2 (&wt)[27], const float2 bb,
+                                           const uint32_t (&a)[9], const bool causal) {
+  float2 acc = bb;
+#pragma unroll
+  for (int r9 = 0; r9 < 9; ++r9) {
+    win[r9][(2 + R) % 3] = lds_f2(a[r9] + R * (PEG_CC * 4));
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) acc = ffma2(win[r9][(kw + R) % 3], wt[r9 * 3 + kw], acc);
+  }
+  const float2 ctr = causal ? win[7][(1 + R) % 3] : win[4][(1 + R) % 3];   // the un-shifted token itself (residual)
+  acc.x += ctr.x; acc.y += ctr.y;
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) peg_tile4_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                        const float* __restrict__ w27,
+                                                        const float* __restrict__ bias, int T, int h, int w,
+                                                        int C, int temporal, int causal, int TT, int HB, int RS) {
+  pdl_sync();
+  extern __shared__ __align__(16) float tile[];      // [(TT+2)][(HB+2)] rows of RS floats ((w+2)*16 + pad)
+  const int N = h * w;
+  const int n_hblk = (h + HB - 1) / HB;
+  const int t0 = (blockIdx.x / n_hblk) * TT, h0 = (blockIdx.x % n_hblk) * HB;
+  const int c0 = blockIdx.y * PEG_CC;
+  const long long bbase = (long long)blockIdx.z * T * N;
+  const int pad_lo = causal ? 2 : 1;
+  const int rows = (TT + 2) * (HB + 2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t inv_T = (65536u + (uint32_t)T - 1u) / (uint32_t)T;       // floor(v / T) == (v * inv_T) >> 16 for v < 65536 / T
+  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+  const int chunks = (w + 2) * 4;                                          // 16-byte chunks per halo row
+  // ---- halo tile: warp <-> halo row; lane <-> 16-byte chunk (consecutive lanes write consecutive shared addresses)
+  for (int pr = warp; pr < rows; pr += nwarps) {
+    const int ph = pr % (HB + 2), pt = pr / (HB + 2);
+    const int t2 = t0 - pad_lo + pt, h2 = h0 - 1 + ph;
+    const bool row_ok = t2 >= 0 && t2 < T && h2 >= 0 && h2 < h;
+    const int fb = row_ok ? (t2 * h + h2) * w : 0;                         // volume position of (t2, h2, w2 = 0)
+    const int tau0 = fb % T, nn0 = fb / T;
+    const uint32_t dst_row = tile_s + (uint32_t)(pr * RS) * 4u;
+    for (int j = lane; j < chunks; j += 32) {
+      const int w2 = (j >> 2) - 1;
+      const bool ok = row_ok && w2 >= 0 && w2 < w;
+      long long row = 0;
+      if (ok) {
+        if (temporal) {
+          const uint32_t v = (uint32_t)(tau0 + w2);
+          const uint32_t q = (v * inv_T) >> 16;
+          row = (long long)(v - q * (uint32_t)T) * N + nn0 + (int)q;
+        } else {
+          row = fb + w2;
+        }
+      }
+      const float* src = x + (bbase + row) * C + c0 + (j & 3) * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_row + (uint32_t)j * 16u), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // ---- strips: weights are fetched while the gather is in flight
+  const int cp = threadIdx.x & 7;                  // channel pair inside the 16-channel slab
+  const int strip = threadIdx.x >> 3;
+  const int sh = strip % HB, st = strip / HB;
+  const bool active = st < TT && t0 + st < T && h0 + sh < h;
+  float2 wt[27];
+  float2 bb = make_float2(0.f, 0.f);
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 27; ++k) wt[k] = __ldg(reinterpret_cast<const float2*>(w27 + (size_t)k * C + c0 + 2 * cp));
+    bb = __ldg(reinterpret_cast<const float2*>(bias + c0 + 2 * cp));
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (!active) return;
+  // shared byte addresses of halo column 0 of the 9 window rows of this strip
+  uint32_t a[9];
+  {
+    const uint32_t base = tile_s + (uint32_t)(((st * (HB + 2) + sh) * RS + 2 * cp) * 4);
+#pragma unroll
+    for (int r9 = 0; r9 < 9; ++r9) a[r9] = base + (uint32_t)((((r9 / 3) * (HB + 2) + r9 % 3) * RS) * 4);
+  }
+  float2 win[9][3];
+#pragma unroll
+  for (int r9 = 0; r9 < 9; ++r9) {
+    win[r9][0] = lds_f2(a[r9]);                     // halo column 0 (w2 = -1)
+    win[r9][1] = lds_f2(a[r9] + PEG_CC * 4);        // halo column 1 (w2 = 0)
+    a[r9] += 2 * PEG_CC * 4;                        // -> the first new column of trip 0 (halo column 2)
+  }
+  // output pointer, advanced incrementally: spatial rows are consecutive; temporal rows follow the literal
+  // reshape  f -> (tau, n) = (f % T, f / T)  ->  canonical row tau * N + n
+  const int fbase = ((t0 + st) * h + (h0 + sh)) * w;
+  int tau = fbase % T;
+  const long long row0 = temporal ? (long long)tau * N + fbase / T : (long long)fbase;
+  float* yp = y + (bbase + row0) * C + c0 + 2 * cp;
+  const long long inc = temporal ? (long long)N * C : (long long)C;
+  const long long wrap = (long long)T * N * C - C;   // temporal: tau T-1 -> 0 moves back T planes and on one token
+  const bool cz = causal != 0;
+#define OMT_PEG_STEP(R)                                                                             \
+  {                                                                                                 \
+    const float2 acc = peg_step<R>(win, wt, bb, a, cz);                                             \
+    *reinterpret_cast<float2*>(yp) = acc;                                                           \
+    yp += inc;                                                                                      \
+    if (temporal && ++tau == T) { tau = 0; yp -= wrap; }                                            \
+  }
+  for (int wb = 0; wb < w; wb += 3) {
+    OMT_PEG_STEP(0)
+    if (wb + 1 < w) OMT_PEG_STEP(1)
+    if (wb + 2 < w) OMT_PEG_STEP(2)
+#pragma unroll
+    for (int r9 = 0; r9 < 9; ++r9) a[r9] += 3 * PEG_CC * 4;
+  }
+#undef OMT_PEG_STEP
+}
+
+// ------------------------------------------------------------------------------------------
 // rope + l2norm + scale, in place on q and k.  One warp per row; lane l owns the complex pair
 // (2l, 2l+1) of every head.
 // ------------------------------------------------------------------------------------------
@@ -534,7 +674,17 @@ extern "C" int omt_peg_volume(const float* x, float* y, const float* w27, const 
   }
   const int threads = ((TT * HB * 8 + 31) / 32) * 32;
   dim3 grid(((T + TT - 1) / TT) * ((h + HB - 1) / HB), C / PEG_CC, B);
-  OMT_CUDA(launch_k(peg_tile_kernel, grid, dim3(threads), smem, (cudaStream_t)stream, x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS));
+  const bool v4 = g_peg_kernel == 4 && T <= 64 && w <= 254 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (v4) {
+    static size_t smem4_set = 0;
+    if (smem > smem4_set) {
+      OMT_CUDA(cudaFuncSetAttribute(peg_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem4_set = smem;
+    }
+    OMT_CUDA(launch_k(peg_tile4_kernel, grid, dim3(threads), smem, (cudaStream_t)stream, x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS));
+  } else {
+    OMT_CUDA(launch_k(peg_tile_kernel, grid, dim3(threads), smem, (cudaStream_t)stream, x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS));
+  }
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }

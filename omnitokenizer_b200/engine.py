@@ -82,6 +82,8 @@ class Engine:
     def __init__(self, model, device: torch.device, math: Optional[str] = None):
         _cabi.load()
         _cabi.set_option("pdl", int(os.environ.get("OMT_PDL", "0")))     # programmatic dependent launch between kernels
+        if os.environ.get("OMT_PEG_KERNEL"):                             # 3 | 4, tuning knob (default: the library's)
+            _cabi.set_option("peg_kernel", int(os.environ["OMT_PEG_KERNEL"]))
         self.device = device
         self.math_name = (math or default_math()).lower()
         if self.math_name not in MATH_MODES:

@@ -30,9 +30,7 @@ def _reset_kernel_options(request):
     try:
         from omnitokenizer_b200 import _cabi
         if _cabi._lib is not None:
-            _cabi.set_option("tc_kernel", 2)
-            _cabi.set_option("tc_block_n", 128)
-            _cabi.set_option("attn_kernel", 3)
-            _cabi.set_option("attn_debug", 0)
+            for name, value in _cabi.DEFAULT_OPTIONS.items():
+                _cabi.set_option(name, value)
     except Exception:
         pass
