@@ -103,7 +103,8 @@ def call(name: str, *args):
 
 
 # process-wide kernel selectors and their library defaults (omt_set_option); tests restore these after flipping them
-DEFAULT_OPTIONS = {"tc_kernel": 2, "tc_block_n": 128, "attn_kernel": 3, "attn_debug": 0, "peg_kernel": 3}
+DEFAULT_OPTIONS = {"tc_kernel": 2, "tc_block_n": 128, "attn_kernel": 3, "attn_debug": 0, "peg_kernel": 3,
+                   "tc_arrive_cta": 1}
 
 
 def set_option(name: str, value: int):

@@ -309,11 +309,12 @@ int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math,
 
 }  // namespace omt
 
-namespace omt { extern int g_attn_kernel; extern int g_attn_debug; extern int g_peg_kernel; }
+namespace omt { extern int g_attn_kernel; extern int g_attn_debug; extern int g_peg_kernel; extern int g_tc2_arrive_cta; }
 
 extern "C" int omt_set_option(const char* name, int value) {
   if (name == nullptr) return OMT_E_ARG;
   if (strcmp(name, "pdl") == 0) { omt::g_pdl = value ? 1 : 0; return OMT_OK; }
+  if (strcmp(name, "tc_arrive_cta") == 0) { omt::g_tc2_arrive_cta = value ? 1 : 0; return OMT_OK; }
   if (strcmp(name, "peg_kernel") == 0) {
     if (value != 3 && value != 4) { omt::set_error("peg_kernel must be 3 or 4"); return OMT_E_ARG; }
     omt::g_peg_kernel = value;

@@ -51,9 +51,18 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on a barrier that may live in the peer CTA (cluster-space address)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a barrier that may live in the peer CTA (cluster-space address).
+// cta_scope = true: default semantics (.release.cta), the form CUTLASS's ClusterBarrier::arrive uses for the 2-SM
+//   pipelines.  What the arrive orders here is this CTA's shared-memory / TMEM traffic (made visible to the async
+//   proxy by the preceding fence.proxy.async / tcgen05.wait::ld); no global memory is published.
+// cta_scope = false: .release.cluster, which ptxas lowers to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR before the arrive --
+//   ncu: 15 % of all stall samples of the FF1 GEMM sit on that sequence in the transform warps, i.e. on the
+//   TMA -> transform -> MMA critical path of every k-block.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr, bool cta_scope) {
+  if (cta_scope)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  else
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // W half: data lands in THIS CTA's smem, the transaction bytes are credited to the LEADER's barrier
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
@@ -92,7 +101,7 @@ template <bool QKV>     // QKV: the epilogue applies rope + l2norm + scale to th
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, const GemmArgs g,
-                const int epilogue, const int num_m_blk, const int num_n_blk, const int n_split) {
+                const int epilogue, const int num_m_blk, const int num_n_blk, const int n_split, const int arrive_cta) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t a_full[STAGES];      // local: this CTA's A stage landed
@@ -228,7 +237,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&ready[s]), 0));
+        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&ready[s]), 0), arrive_cta != 0);
       }
     }
   } else {
@@ -381,7 +390,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tmem_empty[acc]), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tmem_empty[acc]), 0), arrive_cta != 0);
     }
   }
   // ---- teardown: nobody may leave while the peer can still signal our barriers / read our smem
@@ -418,6 +427,8 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 }
 
 }  // namespace tc2
+
+int g_tc2_arrive_cta = 1;   // omt_set_option("tc_arrive_cta", 0|1): scope of the remote mbarrier arrives (see mbar_arrive_cluster)
 
 int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st, const float* A2, int n_split) {
   using namespace tc2;
@@ -475,9 +486,9 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
   cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
   const int ns = A2 != nullptr ? n_split : 0x7fffffff;
   if (epilogue == OMT_EPI_QKV)
-    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns));
+    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns, g_tc2_arrive_cta));
   else
-    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<false>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns));
+    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<false>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns, g_tc2_arrive_cta));
   return OMT_OK;
 }
 

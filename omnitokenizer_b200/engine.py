@@ -82,6 +82,8 @@ class Engine:
     def __init__(self, model, device: torch.device, math: Optional[str] = None):
         _cabi.load()
         _cabi.set_option("pdl", int(os.environ.get("OMT_PDL", "0")))     # programmatic dependent launch between kernels
+        if os.environ.get("OMT_TC_ARRIVE_CTA"):                          # 0 | 1, scope of gemm_tc2's remote mbarrier arrives
+            _cabi.set_option("tc_arrive_cta", int(os.environ["OMT_TC_ARRIVE_CTA"]))
         if os.environ.get("OMT_PEG_KERNEL"):                             # 3 | 4, tuning knob (default: the library's)
             _cabi.set_option("peg_kernel", int(os.environ["OMT_PEG_KERNEL"]))
         self.device = device

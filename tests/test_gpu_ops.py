@@ -105,6 +105,31 @@ def test_linear_geglu_and_rowmaps(cuda, math):
     assert (Xo.cpu().view(B, T, N, 512) - want).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(20480, 1024, 1376), (5120, 512, 512), (40960, 512, 512)])
+def test_linear_remote_arrive_scope(cuda, M, N, K):
+    """gemm_tc2: the remote mbarrier arrives with CTA scope (default, no MEMBAR.ALL.GPU on the k-block critical
+    path) and with cluster scope must give the same bits, run after run, over several waves of tiles per cluster."""
+    cabi = _cabi()
+    from omnitokenizer_b200 import layout as L
+    A = (torch.rand((M, K), device=cuda, generator=torch.Generator(device=cuda).manual_seed(31)) - 0.5)
+    W = (torch.rand((N, K), device=cuda, generator=torch.Generator(device=cuda).manual_seed(32)) - 0.5) * 0.05
+    R = (torch.rand((M, N), device=cuda, generator=torch.Generator(device=cuda).manual_seed(33)) - 0.5)
+    hi = L.tf32_round(W)
+    lo = (W - hi).contiguous()
+    outs = []
+    for scope in (0, 1, 1, 0, 1):
+        cabi.set_option("tc_arrive_cta", scope)
+        out = torch.full((M, N), float("nan"), device=cuda)
+        cabi.call("omt_linear", A, K, 0, 0, 0, hi, lo, out, N, 0, 0, 0, M, N, K, None, R, N, cabi.EPI_NONE,
+                  cabi.MATH_3XTF32)
+        outs.append(out)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ref = (A[:256].double() @ W.double().t() + R[:256].double()).float()
+    assert (outs[0][:256] - ref).abs().max().item() < 2e-5
+
+
 def test_layernorm_and_patchify(cuda):
     cabi = _cabi()
     x = _rand((300, 512), 10, 3.0)
