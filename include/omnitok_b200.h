@@ -162,7 +162,10 @@ int omt_post_vq(const int64_t* idx, const float* E, const float* zc, const float
  * "attn_kernel" = 3 (default: tcgen05 3xTF32 spatial attention core, P as TMEM operand, when N % 128 == 0)
  * | 2 (tcgen05, all operands in shared memory) | 1 (CUDA-core fp32);  "attn_debug": developer knob of kernel 2;
  * "pdl" = 0 (default; measured 2-4 % slower when on) | 1: launch with programmatic dependent launch so a kernel's prologue overlaps the tail of
- * its predecessor (every kernel executes griddepcontrol.wait before its first global-memory access). */
+ * its predecessor (every kernel executes griddepcontrol.wait before its first global-memory access);
+ * "tc_arrive_cta" = 1 (default) | 0: scope of kernel 2's remote mbarrier arrives (0 = .release.cluster, which costs a
+ * MEMBAR.ALL.GPU per k-block: 8 % of the whole step);  "peg_kernel" = 3 (default) | 4 (cp.async gather + packed
+ * f32x2 FMAs; bit-identical, faster only when the input is not L2-resident). */
 int omt_set_option(const char* name, int value);
 
 /* hi/lo split used by the tcgen05 3xTF32 path: lo = x - tf32_trunc(x) (elementwise, n % 4 == 0). */
