@@ -37,6 +37,17 @@ SD = Dict[str, Tensor]
 # gather-form PEG / materialised attention below.  tests/test_oracle.py checks both forms agree.
 USE_LIBRARY_OPS = False
 
+# Numerics-model hook (tests only): when set, every matrix product that the CUDA path runs on the tensor cores --
+# the nn.Linear layers routed through omt_linear and the spatial attention core -- is computed by
+# MATMUL_MODEL(a, b) instead of ``a @ b``; tests/test_oracle.py plugs in an emulation of the kernels' 3xTF32
+# arithmetic to show on the CPU that it keeps the code indices bit-exact.
+MATMUL_MODEL = None
+
+
+def _mm(a: Tensor, b: Tensor) -> Tensor:
+    return a @ b if MATMUL_MODEL is None else MATMUL_MODEL(a, b)
+
+
 
 @dataclass
 class Config:
@@ -136,7 +147,7 @@ def patch_embed(sd: SD, cfg: Config, video: Tensor) -> Tensor:
 
     def emb(x, pre):
         x = layer_norm(x, sd[pre + ".1.weight"], sd[pre + ".1.bias"])
-        x = x @ sd[pre + ".2.weight"].t() + sd[pre + ".2.bias"]
+        x = _mm(x, sd[pre + ".2.weight"].t()) + sd[pre + ".2.bias"]
         return layer_norm(x, sd[pre + ".3.weight"], sd[pre + ".3.bias"])
 
     tok = emb(first, "encoder.to_patch_emb_first_frame")
@@ -187,10 +198,10 @@ def to_pixels(sd: SD, cfg: Config, X: Tensor, hw: Tuple[int, int]) -> Tensor:
     B, T, N, C = X.shape
     h, w = hw
     tok = X.reshape(B, T, h, w, C)
-    f = tok[:, :1] @ sd["decoder.to_pixels_first_frame.0.weight"].t() + sd["decoder.to_pixels_first_frame.0.bias"]
+    f = _mm(tok[:, :1], sd["decoder.to_pixels_first_frame.0.weight"].t()) + sd["decoder.to_pixels_first_frame.0.bias"]
     r = None
     if T > 1:
-        r = tok[:, 1:] @ sd["decoder.to_pixels.0.weight"].t() + sd["decoder.to_pixels.0.bias"]
+        r = _mm(tok[:, 1:], sd["decoder.to_pixels.0.weight"].t()) + sd["decoder.to_pixels.0.bias"]
     return unpatchify(f, r, cfg.image_channels, cfg.patch_size, cfg.temporal_patch_size)
 
 
@@ -289,8 +300,8 @@ def attention_t(sd: SD, pre: str, cfg: Config, X: Tensor, temporal: bool, causal
     B, T, N, C = X.shape
     H, D = cfg.heads, cfg.dim_head
     xn = layer_norm(X, sd[pre + ".norm.gamma"], sd[pre + ".norm.beta"])
-    q = xn @ sd[pre + ".to_q.weight"].t()
-    kv = X @ sd[pre + ".to_kv.weight"].t()
+    q = _mm(xn, sd[pre + ".to_q.weight"].t())
+    kv = _mm(X, sd[pre + ".to_kv.weight"].t())
     k, v = kv[..., : H * D], kv[..., H * D:]
     q, k, v = (t.reshape(B, T, N, H, D) for t in (q, k, v))
     if (not temporal) and cfg.spatial_pos == "rope":
@@ -305,14 +316,16 @@ def attention_t(sd: SD, pre: str, cfg: Config, X: Tensor, temporal: bool, causal
     if USE_LIBRARY_OPS:
         o = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=causal, scale=8)
     else:
-        s = (q @ k.transpose(-1, -2)) * 8.0
+        tc_core = (not temporal) and N % 128 == 0        # the shapes attn_tc3_kernel takes (tensor-core core)
+        mm = _mm if tc_core else torch.matmul
+        s = mm(q, k.transpose(-1, -2)) * 8.0
         if causal:
             L = s.shape[-1]
             mask = torch.ones(L, L, dtype=torch.bool).triu(1)
             s = s.masked_fill(mask, float("-inf"))
-        o = torch.softmax(s, dim=-1) @ v
+        o = mm(torch.softmax(s, dim=-1), v)
     o = o.permute(0, 3, 1, 2, 4) if temporal else o.permute(0, 1, 3, 2, 4)      # -> (B,T,N,H,D)
-    return o.reshape(B, T, N, H * D) @ sd[pre + ".to_out.weight"].t()
+    return _mm(o.reshape(B, T, N, H * D), sd[pre + ".to_out.weight"].t())
 
 
 def window_rows(h: int, w: int, ws: int) -> Tensor:
@@ -328,13 +341,13 @@ def window_attention(sd: SD, pre: str, cfg: Config, X: Tensor, hw: Tuple[int, in
     xn = layer_norm(X, sd[pre + ".norm.gamma"], sd[pre + ".norm.beta"])
     rows = window_rows(hw[0], hw[1], ws)                                        # (nW, 64)
     xw = xn[:, :, rows]                                                         # (B,T,nW,64,C)
-    qkv = (xw @ sd[pre + ".qkv.weight"].t()).reshape(B, T, rows.shape[0], ws * ws, 3, H, D)
+    qkv = _mm(xw, sd[pre + ".qkv.weight"].t()).reshape(B, T, rows.shape[0], ws * ws, 3, H, D)
     q, k, v = (qkv[..., i, :, :].permute(0, 1, 2, 4, 3, 5) for i in range(3))   # (B,T,nW,H,64,D)
     s = (q * (D ** -0.5)) @ k.transpose(-1, -2)
     bias = sd[pre + ".relative_position_bias_table"][sd[pre + ".relative_position_index"].reshape(-1)]
     s = s + bias.reshape(ws * ws, ws * ws, H).permute(2, 0, 1)
     o = (torch.softmax(s, dim=-1) @ v).permute(0, 1, 2, 4, 3, 5).reshape(B, T, rows.shape[0], ws * ws, C)
-    o = o @ sd[pre + ".proj.weight"].t() + sd[pre + ".proj.bias"]
+    o = _mm(o, sd[pre + ".proj.weight"].t()) + sd[pre + ".proj.bias"]
     out = torch.empty_like(X)
     out[:, :, rows] = o
     return out
@@ -343,9 +356,9 @@ def window_attention(sd: SD, pre: str, cfg: Config, X: Tensor, hw: Tuple[int, in
 def feed_forward(sd: SD, pre: str, cfg: Config, X: Tensor) -> Tensor:
     """modules/attention.py:153-168: LN -> Linear(512,2730) -> gelu(gate)*x -> Linear(1365,512)."""
     inner = sd[pre + ".4.weight"].shape[1]
-    y = layer_norm(X, sd[pre + ".0.weight"], sd[pre + ".0.bias"]) @ sd[pre + ".1.weight"].t()
+    y = _mm(layer_norm(X, sd[pre + ".0.weight"], sd[pre + ".0.bias"]), sd[pre + ".1.weight"].t())
     u = gelu_erf(y[..., inner:]) * y[..., :inner]
-    return u @ sd[pre + ".4.weight"].t()
+    return _mm(u, sd[pre + ".4.weight"].t())
 
 
 def transformer(sd: SD, pre: str, cfg: Config, X: Tensor, hw: Tuple[int, int], block: str,

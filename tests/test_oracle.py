@@ -107,3 +107,54 @@ def test_library_op_form_agrees_with_restatement():
         oo.USE_LIBRARY_OPS = False
     assert torch.equal(idx, fx["idx"].long())
     check_sub(fx["rec"], rec, 2e-5, "reconstruction (library-op form)")
+
+
+# ---- numerics model of the tensor-core path -------------------------------------------------
+def _tf32_rna(x):
+    """round-to-nearest (ties away) to 10 explicit mantissa bits: the kernels' tf32_rn / layout.tf32_round."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _tf32_trunc(x):
+    """what the tensor core does to an fp32 operand of a kind::tf32 MMA: the low 13 mantissa bits are ignored."""
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def _mm_3xtf32(a, b):
+    ah, bh = _tf32_rna(a), _tf32_rna(b)
+    al, bl = _tf32_trunc(a - ah), _tf32_trunc(b - bh)
+    return (al @ bh + ah @ bl) + ah @ bh          # the kernels' order: A_lo.W_hi, A_hi.W_lo, A_hi.W_hi, fp32 accumulate
+
+
+def _mm_tf32(a, b):
+    return _tf32_trunc(a) @ _tf32_trunc(b)
+
+
+def test_layout_tf32_round_is_rna():
+    from omnitokenizer_b200 import layout as L
+    x = torch.randn(4096, generator=torch.Generator().manual_seed(3)) * 3.0
+    assert torch.equal(L.tf32_round(x), _tf32_rna(x))
+    lo = x - L.tf32_round(x)
+    assert (lo.abs() <= x.abs() * 2.0 ** -11 * (1 + 1e-6)).all()        # |lo| <= half a tf32 ulp
+    assert torch.equal(L.tf32_round(x) + lo, x)                          # the split is lossless in fp32
+
+
+@pytest.mark.parametrize("name", ["vid9x128_b2", "img256_cfg1"])
+def test_3xtf32_numerics_model_keeps_code_indices(name, monkeypatch):
+    """Every tensor-core product of the CUDA path (nn.Linear layers + spatial attention core) replaced by an
+    emulation of 3xTF32 (hi/lo split, three fp32-accumulated products): indices stay bit-exact vs the reference's
+    golden vectors and pixels stay within 1e-3 (north_star).  Single-pass TF32 is ~1000x less accurate: it is a
+    throughput mode only (on the GPU it flips ~6/5120 indices of cfg-3)."""
+    fx = load_golden(name)
+    cfg, sd, x = golden_setup(fx)
+    is_image = x.ndim == 4
+    err = {}
+    with torch.no_grad():
+        for label, model in (("3xtf32", _mm_3xtf32), ("tf32", _mm_tf32)):
+            monkeypatch.setattr(oo, "MATMUL_MODEL", model)
+            emb, idx = oo.encode(sd, cfg, x, include_embeddings=True)
+            rec = oo.decode(sd, cfg, fx["idx"].long(), is_image)      # decode the reference's codes: isolates decoder error
+            err[label] = (int((idx != fx["idx"].long()).sum()), check_sub(fx["rec"], rec, 1.0, "reconstruction"))
+    assert err["3xtf32"][0] == 0, f"3xTF32 model flipped {err['3xtf32'][0]} indices"
+    assert err["3xtf32"][1] <= 1e-4, err
+    assert err["tf32"][1] > 20 * err["3xtf32"][1], err                 # the single-pass mode is far off fp32 grade
