@@ -22,7 +22,7 @@ Reference citations are relative to /root/reference/OmniTokenizer/.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
 import torch

@@ -1,6 +1,6 @@
 """Launch the dominant GEMM (FF1 + GEGLU, M=40960 N=2752 K=512) a few times for `ncu --set full`,
 and time variants with CUDA events (not under ncu)."""
-import os, sys, json
+import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from omnitokenizer_b200 import _cabi, layout as L

@@ -1,7 +1,5 @@
 """CPU tests of the drop-in boundary: key layout, arg surface, C-ABI symbols, host-side index maps."""
 import argparse
-import ctypes
-import json
 import os
 import re
 

@@ -1,6 +1,5 @@
 """GPU op-level parity: every C-ABI kernel vs the oracle's restatement of the same reference op.
 Tolerances are fp32 round-off (different summation order), written next to each check."""
-import os
 
 import pytest
 import torch

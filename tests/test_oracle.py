@@ -6,7 +6,7 @@ import torch
 from oracle import omni_oracle as oo
 from oracle import ref_loader as rl
 from oracle import weights as W
-from tests.util import GOLDEN_CASES, check_sub, golden_setup, load_golden
+from tests.util import check_sub, golden_setup, load_golden
 
 FAST = ["img64", "vid5x64", "vae_vid5x64", "vae_img64", "cnn_vid5x64"]
 

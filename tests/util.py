@@ -1,5 +1,4 @@
 """Shared helpers for the parity tests (oracle = oracle/omni_oracle.py, test infrastructure)."""
-import argparse
 import os
 
 import torch
