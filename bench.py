@@ -1,16 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- video-frames/s of OmniTokenizer_VQGAN encode -> codes -> decode (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4|cfg5]
+                    [--math f16x3|3xtf32|fp32]
 
 Workload (config.workload): cfg3 = batch of 8 synthetic videos 17x256x256 (the configuration the
 metric is quoted on, BASELINE.json configs[2]); under torchrun the batch is split over ranks
 (strong scaling), each rank encodes its shard, ONE all-gather of code indices, decode of the shard.
+cfg2 (64 images), cfg4 (4 videos 33x512x512: ranks beyond the batch idle, "replicas only beyond B") and
+cfg5 (cfg3 in VAE mode: no codes, hence no collective) are BASELINE.json's other configurations.
 A "step" is one pass of that path over the batch.  Prints ONE JSON line (rank 0).
 
 --impl reference: the CPU baseline arm -- the oracle port of the reference's PyTorch path
-(oracle/omni_oracle.py; the reference tree itself does not travel to the GPU box) on all host
-threads, each step a bounded sample (one 17x256x256 video) of the same workload.
+(oracle/omni_oracle.py; the reference tree itself does not travel to the GPU box) on the host
+threads, every step the SAME full batch and the same weights as the GPU arm.
 """
 import argparse
 import json
@@ -28,9 +31,11 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "cfg3": dict(shape=(8, 3, 17, 256, 256), desc="batch=8 videos 17x256x256 (UCF-shaped synthetic), VQVAE"),
     "cfg2": dict(shape=(64, 3, 256, 256), desc="batch=64 images 256x256, VQVAE"),
+    "cfg4": dict(shape=(4, 3, 33, 512, 512), desc="batch=4 videos 33x512x512 (long-sequence stress), VQVAE"),
+    "cfg5": dict(shape=(8, 3, 17, 256, 256), desc="batch=8 videos 17x256x256, VAE mode (use_vae, KL path, no codebook argmin)", vae=True),
 }
 # algorithmic FLOPs per batch: enc+dec, un-padded dims
-TFLOP = {"cfg3": 4.729, "cfg2": 7.500}
+TFLOP = {"cfg3": 4.729, "cfg2": 7.500, "cfg4": 22.615, "cfg5": 4.724}
 
 
 def peaks():
@@ -75,10 +80,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def make_model(dev):
+def make_model(dev, vae=False):
     import omnitokenizer_b200 as ob
     torch.manual_seed(0)
-    m = ob.OmniTokenizer_VQGAN(ob.canonical_args())
+    m = ob.OmniTokenizer_VQGAN(ob.canonical_args(["--use_vae"] if vae else []))
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():      # move scales / LN gains off their ones init
         for n, p in m.named_parameters():
@@ -88,66 +93,86 @@ def make_model(dev):
     return m.to(dev).eval()
 
 
-def pick_cpu_threads(sd, x_small):
+def pick_cpu_threads(sd, x_small, vae=False):
     """The oracle's many small torch ops do not scale to every core of a 100+-core host (128 threads is
     ~30x SLOWER than 16 on the B200 box), so take the best of a short sweep; `cores` reports that count."""
     cores = os.cpu_count() or 1
     best, best_t = None, None
     for nt in sorted({min(c, cores) for c in (8, 16, 32, 64)}):
         torch.set_num_threads(nt)
-        cpu_oracle_run(sd, x_small)
-        dt, _, _ = cpu_oracle_run(sd, x_small)
+        cpu_oracle_run(sd, x_small, vae=vae)
+        dt, _, _ = cpu_oracle_run(sd, x_small, vae=vae)
         if best_t is None or dt < best_t:
             best, best_t = nt, dt
     torch.set_num_threads(best)
     return best
 
 
-def cpu_oracle_run(sd, x, reps=1):
+def cpu_oracle_run(sd, x, reps=1, vae=False):
     from oracle import omni_oracle as oo
     oo.USE_LIBRARY_OPS = True      # same torch library calls as the reference (conv3d PEG, SDPA)
-    cfg = oo.Config()
+    cfg = oo.Config(use_vae=vae)
     is_image = x.ndim == 4
     best = None
     with torch.no_grad():
         for _ in range(reps):
             t0 = time.perf_counter()
-            idx = oo.encode(sd, cfg, x)
-            rec = oo.decode(sd, cfg, idx, is_image)
+            if vae:      # encode draws the posterior noise on the CPU generator (vae.py:16); decode takes 'b t h w c' (:313)
+                idx = oo.encode(sd, cfg, x, noise=torch.randn((x.shape[0], 8) + ((1,) if is_image else (1 + (x.shape[2] - 1) // 4,))
+                                                              + (x.shape[-2] // 8, x.shape[-1] // 8)))
+                rec = oo.decode(sd, cfg, idx if is_image else idx.permute(0, 2, 3, 4, 1), is_image)
+            else:
+                idx = oo.encode(sd, cfg, x)
+                rec = oo.decode(sd, cfg, idx, is_image)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     return best, idx, rec
 
 
 def run_reference(args):
-    """CPU arm: oracle port of the reference path on the host cores; rank 0 only."""
+    """CPU arm: oracle port of the reference path on the host cores, the full batch and the GPU arm's weights; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import omnitokenizer_b200 as ob
     wl = WORKLOADS[args.workload]
-    torch.manual_seed(0)
-    m = ob.OmniTokenizer_VQGAN(ob.canonical_args())
+    vae = bool(wl.get("vae"))
+    m = make_model(torch.device("cpu"), vae)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    shape = (1,) + wl["shape"][1:]
+    shape = wl["shape"]
     x = torch.rand(shape, generator=torch.Generator().manual_seed(1234)) - 0.5
-    cores = pick_cpu_threads(sd, x)
-    frames = shape[2] if len(shape) == 5 else 1
-    for _ in range(args.warmup):
-        cpu_oracle_run(sd, x)
+    cores = pick_cpu_threads(sd, x[:1], vae)
+    frames = shape[0] * (shape[2] if len(shape) == 5 else 1)
+    for _ in range(min(args.warmup, 1)):          # one warm pass (a step is ~10 s of host time)
+        cpu_oracle_run(sd, x, vae=vae)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_oracle_run(sd, x)
+        cpu_oracle_run(sd, x, vae=vae)
     dt = time.perf_counter() - t0
     v = frames * args.steps / dt
-    sample = f"1 of {wl['shape'][0]} samples of the batch per step ({'x'.join(map(str, shape))})"
+    sample = (f"the full batch ({'x'.join(map(str, shape))}) every step, same weights as the GPU arm; {cores} torch threads (best of "
+              f"a sweep on this host); one untimed warm pass (a step is ~10 s of host time)")
     print(json.dumps({
         "impl": "reference", "metric": "video_frames_per_sec_encode_decode", "value": round(v, 3), "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"], "sample": sample},
-        "cpu_baseline": {"value": round(v, 3), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": args.workload + ": " + wl["desc"], "global_batch": shape[0], "frames": frames},
+        "cpu_baseline": {"value": round(v, 3), "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": round(v, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def _event_time(fn, flush, reps=10):
+    """median CUDA-event time of fn() in ms, L2 flushed before every repetition"""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i in range(reps + 2):
+        flush.add_(1.0)
+        if i >= 2:
+            evs[i - 2][0].record()
+        fn()
+        if i >= 2:
+            evs[i - 2][1].record()
+    torch.cuda.synchronize()
+    return sorted(a.elapsed_time(b) for a, b in evs)[reps // 2]
 
 
 def time_dominant_kernel(m, M, dev, flush):
@@ -157,20 +182,38 @@ def time_dominant_kernel(m, M, dev, flush):
     eng = m.engine()
     lyr = eng.enc_spatial["layers"][0]
     ws = eng._workspace(M)
-    ws.XN.normal_()
-    reps = 10
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for i in range(reps + 2):
-        flush.add_(1.0)
-        if i >= 2:
-            evs[i - 2][0].record()
-        eng._linear(ws.XN, eng.C, lyr["ff1"], ws.U, eng.ku, M, epi=_cabi.EPI_GEGLU)
-        if i >= 2:
-            evs[i - 2][1].record()
-    torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in evs)[reps // 2]
+    if eng.planes:
+        x = torch.randn(M, eng.C, device=dev)
+        eng._ln_h(x, ws.XNp, lyr["ff_g"], lyr["ff_b"], M)
+        fn = lambda: eng._linear_h(ws.XNp, lyr["ff1"], M, U=ws.Up, epi=_cabi.EPI_GEGLU)
+    else:
+        ws.XN.normal_()
+        fn = lambda: eng._linear(ws.XN, eng.C, lyr["ff1"], ws.U, eng.ku, M, epi=_cabi.EPI_GEGLU)
+    ms = _event_time(fn, flush)
     flops = 2.0 * M * (2 * eng.inner) * eng.C          # un-padded algorithmic FLOPs of Linear(512 -> 2730)
     return ms, flops
+
+
+def time_vq_lookup(m, M, dev, flush):
+    """The codebook nearest-neighbour search alone (BASELINE.json's "VQ-lookup HBM GB/s"): algorithmic bytes =
+    z (M x 8 fp32) + the 8192 x 8 table + int64 indices; FLOPs = 2 * 8 * n_codes per row."""
+    from omnitokenizer_b200 import _cabi
+    eng = m.engine()
+    ws = eng._workspace(M)
+    z = torch.nn.functional.normalize(torch.randn(M, 8, device=dev), dim=1)
+
+    def fn():
+        ws.counts.zero_()
+        _cabi.call("omt_vq_search", z, eng.E, eng.e2, M, eng.n_codes, ws.idx, ws.counts, ws.vqws)
+    ms = _event_time(fn, flush)
+    bytes_ = M * 8 * 4 + eng.n_codes * 8 * 4 + M * 8
+    flops = 2.0 * 8 * eng.n_codes * M
+    sms, _, _ = _cabi.device_info()
+    fp32_peak = sms * 128 * 2 * 1.965e9 / 1e12          # FFMA lanes x 2 flop x max SM clock
+    return {"us": round(ms * 1e3, 1), "hbm_gbs": round(bytes_ / (ms * 1e-3) / 1e9, 2), "algorithmic_bytes": bytes_,
+            "fma_tflops": round(flops / (ms * 1e-3) / 1e12, 2), "fp32_peak_tflops": round(fp32_peak, 1),
+            "frac_fma": round(flops / (ms * 1e-3) / 1e12 / fp32_peak, 3),
+            "note": "FP32-FMA-bound (3.3 kFLOP/B): the HBM figure is reported because the metric names it, the FMA fraction binds"}
 
 
 def main():
@@ -180,7 +223,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--math", default=None, help="fp32 | 3xtf32 | tf32 (default: OMT_MATH or 3xtf32)")
+    ap.add_argument("--math", default=None, help="f16x3 | 3xtf32 | fp32 (default: OMT_MATH or the engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -208,26 +251,30 @@ def main():
     shape = wl["shape"]
     B = shape[0]
     is_image = len(shape) == 4
+    vae = bool(wl.get("vae"))
     frames_per_sample = 1 if is_image else shape[2]
     s, e = od.shard_bounds(B, rank, world)
     x_full = torch.rand(shape, generator=torch.Generator().manual_seed(1234)) - 0.5
     x_host = x_full[s:e].contiguous().pin_memory()
     x_dev = x_host.to(dev)
-    m = make_model(dev)
+    m = make_model(dev, vae)
     m.prepare()
     flush = torch.zeros(64 * 1024 * 1024, device=dev)      # 256 MiB > 126 MB L2
+    gathered = {}
 
     def step(x):
-        if x.shape[0] == 0:
-            codes = torch.empty((0,), dtype=torch.int64, device=dev)
-        else:
-            codes = m.encode(x, is_image)
+        if vae:      # KL path: no code indices, hence no collective; decode takes the channels-last latent (omnitokenizer.py:313)
+            if x.shape[0] == 0:
+                return None
+            z = m.encode(x, is_image)
+            return m.decode(z if is_image else z.permute(0, 2, 3, 4, 1), is_image)
+        codes = m.encode(x, is_image)                       # an empty shard (B < world) returns an empty, right-shaped tensor
         pending = None
         if world > 1 and not os.environ.get("OMT_BENCH_NO_GATHER"):
             pending = od.all_gather_codes_async(codes, B)   # the single collective, overlapped with the local decode
         rec = None if x.shape[0] == 0 else m.decode(codes, is_image)
         if pending is not None:
-            all_codes = pending.wait()                      # every rank now holds the full (B,T',h,w) index tensor
+            gathered["codes"] = pending.wait()              # every rank now holds the full (B,T',h,w) index tensor
         return rec
 
     def barrier():
@@ -253,6 +300,15 @@ def main():
     barrier()
     launches = _cabi.launch_count - n0
     t_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # the gathered codes of the last step must be the single-GPU codes of the full batch (checked once, untimed)
+    gather_ok = None
+    if world > 1 and not vae and "codes" in gathered:
+        ok = torch.ones(1, device=dev)
+        if rank == 0:
+            full = m.encode(x_full.to(dev), is_image)
+            ok[0] = float(torch.equal(full, gathered["codes"]))
+        dist.broadcast(ok, 0)
+        gather_ok = bool(ok.item())
     # ---- e2e: pinned host input -> H2D -> encode -> decode -> D2H of the reconstruction, every step ----
     # Serving-style pipeline through the public API: the H2D copy of step i+1 and the D2H copy of step i-1 run on
     # their own streams (separate DMA engines) while step i computes; all copies are inside the timed region
@@ -331,20 +387,22 @@ def main():
         achieved = k_flops / (k_ms * 1e-3) / 1e12
         traffic = None
         try:      # dram__bytes_read+write of this launch from the committed `ncu --set full` capture (cfg-3, N=1)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_ff1_traffic.json")))
-            if world == 1 and args.workload == "cfg3" and not os.environ.get("OMT_BENCH_BATCH") and math == tj.get("math"):
-                traffic = tj["dram_bytes"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_ff1_traffic.json")))
+            if world == 1 and args.workload in ("cfg3", "cfg5") and not os.environ.get("OMT_BENCH_BATCH") and math in tj:
+                traffic = tj[math]["dram_bytes"]
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": f"gemm_tc2_kernel[{math}] FF1+GEGLU M={M_local} N=2730 K=512" if math == "3xtf32"
-                else (f"gemm_tc_kernel[{math}] FF1+GEGLU M={M_local} N=2730 K=512" if math == "tf32"
-                      else f"gemm_fp32_kernel FF1+GEGLU M={M_local} N=2730 K=512"),
+        kname = {"3xtf32": "gemm_tc2_kernel", "f16x3": "gemm_f16_kernel", "fp32": "gemm_fp32_kernel"}[math]
+        own = {"3xtf32": "3xTF32 issues 3 tf32 MMAs per product: its own ceiling is 1/3 of this",
+               "f16x3": "f16x3 issues 3 kind::f16 MMAs (2x the tf32 rate) per product: its own ceiling is 2/3 of this",
+               "fp32": "CUDA-core FFMA kernel: bounded by the fp32 pipe, not the tensor pipe"}[math]
+        roof = {"bound": "tensor", "kernel": f"{kname}[{math}] FF1+GEGLU M={M_local} N=2730 K=512",
                 "achieved": round(achieved, 2), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                 "frac": round(achieved / tf32_peak, 4), "traffic": traffic,
-                "algorithmic_bytes": int(M_local * 512 * 4 + 2 * 2752 * 512 * 4 + M_local * 1376 * 4),
+                "algorithmic_bytes": int(M_local * 512 * 4 + 2 * 2730 * 512 * 4 + M_local * 1365 * 4),
                 "ms_per_launch": round(k_ms, 4),
                 "peak_note": f"tf32 dense = 0.5 x {pk_src} bf16 burst {pk['bf16_tflops']} TF/s; FLOPs are algorithmic fp32 "
-                             f"(2MNK); 3xTF32 issues 3 MMAs per product so its own ceiling is 1/3 of this",
+                             f"(2MNK); {own}",
                 "whole_path": {"tflop_per_batch": TFLOP[args.workload],
                                "achieved_tflops": round(TFLOP[args.workload] * args.steps / (t_ms / 1e3), 2)}}
         line = {
@@ -352,7 +410,10 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_ms / args.steps, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "global_batch": B, "frames": frames,
-                       "parallelism": f"batch-shard dp{world}, 1 all-gather of code indices", "math": math,
+                       "parallelism": (f"batch-shard dp{world}, no collective (VAE latents stay local)" if vae else
+                                       f"batch-shard dp{world}, 1 all-gather of code indices")
+                                      + (f"; {world - B} ranks idle (replicas only beyond B)" if world > B else ""),
+                       "math": math,
                        "l2": "256 MiB flush between timed steps (untimed); activations >> L2"},
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": out_host[0].numel() * 4, "ms_per_step": round(t2_ms / e2e_steps, 3),
@@ -360,19 +421,29 @@ def main():
                     "host_link": link},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
+        if gather_ok is not None:
+            line["gathered_codes_equal_single_gpu"] = gather_ok
+        if not vae and M_local > 0:
+            line["vq_lookup"] = time_vq_lookup(m, M_local, dev, flush)
         if not args.no_cpu_baseline and world == 1:
             sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
             xs = x_full[:1]
-            cores = pick_cpu_threads(sd, xs)
-            cpu_oracle_run(sd, xs)                              # warm-up
-            dt, idx_o, rec_o = cpu_oracle_run(sd, xs, reps=2)
+            cores = pick_cpu_threads(sd, xs, vae)
+            cpu_oracle_run(sd, xs, vae=vae)                     # warm-up
+            torch.manual_seed(7)
+            dt, idx_o, rec_o = cpu_oracle_run(sd, xs, reps=1, vae=vae)
+            torch.manual_seed(7)                                # VAE: the same CPU-generator noise draw on both sides
             idx_g = m.encode(xs.to(dev), is_image)
-            rec_g = m.decode(idx_g, is_image)
+            rec_g = m.decode(idx_g if (is_image or not vae) else idx_g.permute(0, 2, 3, 4, 1), is_image)
             line["cpu_baseline"] = {"value": round(frames_per_sample / dt, 3), "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(),
                                     "kind": "port",
-                                    "sample": f"1 of {B} samples ({'x'.join(map(str, xs.shape))}), best of 2 after warm-up"}
-            line["parity"] = {"idx_mismatch": int((idx_g.cpu() != idx_o).sum()), "n_idx": idx_o.numel(),
-                              "max_abs_pixel_err": float((rec_g.cpu() - rec_o).abs().max())}
+                                    "sample": f"1 of {B} samples ({'x'.join(map(str, xs.shape))}), one pass after warm-up"}
+            if vae:
+                line["parity"] = {"max_abs_latent_err": float((idx_g.cpu() - idx_o).abs().max()),
+                                  "max_abs_pixel_err": float((rec_g.cpu() - rec_o).abs().max())}
+            else:
+                line["parity"] = {"idx_mismatch": int((idx_g.cpu() != idx_o).sum()), "n_idx": idx_o.numel(),
+                                  "max_abs_pixel_err": float((rec_g.cpu() - rec_o).abs().max())}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

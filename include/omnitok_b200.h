@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OMT_ABI_VERSION 1
+#define OMT_ABI_VERSION 2
 
 #define OMT_OK 0
 #define OMT_E_ARG (-1)    /* bad shape / alignment / null pointer */
@@ -50,7 +50,7 @@ int omt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* GEMM math selectors */
 #define OMT_MATH_FP32 0      /* CUDA-core FFMA, exact fp32 (parity anchor) */
 #define OMT_MATH_3XTF32 1    /* tcgen05 kind::tf32, error-compensated hi/lo split, fp32 accumulate in TMEM */
-#define OMT_MATH_TF32 2      /* tcgen05 kind::tf32 single pass (throughput mode; NOT index-exact) */
+#define OMT_MATH_F16X3 3     /* tcgen05 kind::f16 on pre-split fp16 hi / bf16 lo operand planes (omt_linear_h) */
 
 /* C[M, N] = A[M, K] . W[N, K]^T (+ bias[N]) (+ residual[M, N]); nn.Linear everywhere on the path:
  * attention.py:411 (to_q / to_kv), :486 (to_out), :271/:288 (window qkv / proj), :164/:167 (FF),
@@ -59,7 +59,7 @@ int omt_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * or K % 32 == 0 (tcgen05 paths).  With OMT_EPI_GEGLU, N counts packed columns and C has N/2 columns.
  * residual may alias C (same ld): out-of-place is not required.  For OMT_MATH_3XTF32 `W` must be the
  * tf32-rounded (round-to-nearest, low 13 mantissa bits zero) high part of the weight and `W_lo` the
- * exact remainder (same shape); W_lo is ignored (may be NULL) for FP32 / TF32. */
+ * exact remainder (same shape); W_lo is ignored (may be NULL) for FP32. */
 int omt_linear(const float* A, int lda, int a_seg, int a_seg_stride, int a_seg_off,
                const float* W, const float* W_lo,
                float* C, int ldc, int c_seg, int c_seg_stride, int c_seg_off,
@@ -89,8 +89,9 @@ int omt_layernorm(const float* x, int ldx, float* y, int ldy, const float* w, co
 /* Patch gather + LayerNorm (omnitokenizer.py:806-808 / :814-817: Rearrange + nn.LayerNorm).
  * video (B, Cin, T, H, W) fp32 contiguous.  first=1: frame 0, rows (b,h,w), features (c,p1,p2);
  * first=0: frames 1.., rows (b,t,h,w), features (c,pt,p1,p2).  A is [rows, K] dense.
- * ln_w == ln_b == NULL: plain patch gather (im2col of the strided Conv3d of patch_embed='cnn', omnitokenizer.py:823-838). */
-int omt_patchify_ln(const float* video, float* A, const float* ln_w, const float* ln_b,
+ * ln_w == ln_b == NULL: plain patch gather (im2col of the strided Conv3d of patch_embed='cnn', omnitokenizer.py:823-838).
+ * A_hi != NULL: the rows are written as fp16 hi / bf16 lo operand planes [rows, K] instead of A (A may be NULL). */
+int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uint16_t* A_lo, const float* ln_w, const float* ln_b,
                     int B, int Cin, int T, int H, int W, int p, int pt, int first, float eps,
                     omt_stream_t stream);
 
@@ -120,21 +121,24 @@ int omt_qk_prep(float* q, int ldq, float* k, int ldk, const float* q_scale, cons
                 omt_stream_t stream);
 
 /* Full (non-causal) attention over n_seq sequences of N contiguous canonical rows, head dim 64:
- * o = softmax(scale * q k^T) v   (attention.py:451, SDPA branch: no additive bias).  N % 64 == 0. */
+ * o = softmax(scale * q k^T) v   (attention.py:451, SDPA branch: no additive bias).  N % 64 == 0.
+ * All three attention cores: when o_hi != NULL the result is written as fp16 hi / bf16 lo operand planes
+ * (leading dimension ldo) for the out-projection GEMM instead of fp32 o (o may then be NULL). */
 int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                     float* o, int ldo, int n_seq, int N, int heads, float scale, omt_stream_t stream);
+                     float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, int n_seq, int N, int heads, float scale,
+                     omt_stream_t stream);
 
 /* 8x8 (ws x ws, ws*ws == 64) window attention with relative position bias (attention.py:254-286):
  * o = softmax(scale * q k^T + bias[head]) v within each window of the (h, w) token grid.
  * bias: [heads, 64, 64] already gathered from the 225-entry table. */
 int omt_attn_window(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                    float* o, int ldo, const float* bias, int n_frames, int h, int w, int ws, int heads,
+                    float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, const float* bias, int n_frames, int h, int w, int ws, int heads,
                     float scale, omt_stream_t stream);
 
 /* Temporal attention: for every (b, n) a sequence over t' (rows b*T*N + t*N + n), optional causal
  * mask (attention.py:451 is_causal); 1 <= T <= 17. */
 int omt_attn_temporal(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                      float* o, int ldo, int B, int T, int N, int heads, float scale, int causal,
+                      float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, int B, int T, int N, int heads, float scale, int causal,
                       omt_stream_t stream);
 
 /* pre_vq_conv (omnitokenizer.py:144-154) [+ F.normalize(dim=channels) :251-252]:
@@ -157,19 +161,42 @@ int omt_post_vq(const int64_t* idx, const float* E, const float* zc, const float
                 float* zq_out, const float* Wt, const float* b, float* X, int M, int C, int cd,
                 omt_stream_t stream);
 
-/* Tuning knobs (process-wide).  "tc_kernel" = 2 (default: persistent 2-CTA cta_group::2 kernel for
- * 3xTF32) | 1 (one tile per CTA);  "tc_block_n" = 128 | 256: tile-N of kernel 1;
- * "attn_kernel" = 3 (default: tcgen05 3xTF32 spatial attention core, P as TMEM operand, when N % 128 == 0)
- * | 2 (tcgen05, all operands in shared memory) | 1 (CUDA-core fp32);  "attn_debug": developer knob of kernel 2;
- * "pdl" = 0 (default; measured 2-4 % slower when on) | 1: launch with programmatic dependent launch so a kernel's prologue overlaps the tail of
- * its predecessor (every kernel executes griddepcontrol.wait before its first global-memory access);
- * "tc_arrive_cta" = 1 (default) | 0: scope of kernel 2's remote mbarrier arrives (0 = .release.cluster, which costs a
- * MEMBAR.ALL.GPU per k-block: 8 % of the whole step);  "peg_kernel" = 3 (default) | 4 (cp.async gather + packed
- * f32x2 FMAs; bit-identical, faster only when the input is not L2-resident). */
-int omt_set_option(const char* name, int value);
+/* ---- f16x3 path: operands as 16-bit planes ------------------------------------------------------------
+ * An fp32 matrix X is carried as hi = fp16(X) (round to nearest, saturating) and lo = bf16(X - hi), two
+ * uint16 matrices with a common leading dimension.  Producers below write the planes directly; weights are
+ * split once on the host.  ("f16_scheme" = 2 switches the lo planes to fp16((X - hi) * 2^11), see omt_set_option.) */
+typedef struct omt_linear_h_args {
+  const uint16_t* a_hi; const uint16_t* a_lo;      /* A planes [M, lda] */
+  const uint16_t* a2_hi; const uint16_t* a2_lo;    /* optional second A (dual-A form, columns >= n_split), same lda / row map */
+  int n_split;                                     /* multiple of 256 */
+  int lda, a_seg, a_seg_stride, a_seg_off;         /* lda % 8 == 0; row map as in omt_linear (segments of 64 rows) */
+  const uint16_t* w_hi; const uint16_t* w_lo;      /* W planes [N rounded up to 256, K], K % 64 == 0 */
+  float* c; int ldc, c_seg, c_seg_stride, c_seg_off;   /* fp32 output (OMT_EPI_NONE / OMT_EPI_QKV); row map segments of 32 rows */
+  uint16_t* u_hi; uint16_t* u_lo; int ldu;         /* OMT_EPI_GEGLU: output planes U[M, N/2] */
+  int M, N, K;
+  const float* bias; const float* residual; int ldr;   /* residual may alias c */
+  int epilogue;
+  const float* q_scale; const float* k_scale; const float* rope_cos; const float* rope_sin;   /* OMT_EPI_QKV, as omt_linear2 */
+  int qk_cols, tokens;
+} omt_linear_h_args;
 
-/* hi/lo split used by the tcgen05 3xTF32 path: lo = x - tf32_trunc(x) (elementwise, n % 4 == 0). */
-int omt_split_lo(const float* x, float* lo, int64_t n, omt_stream_t stream);
+/* Same contract as omt_linear / omt_linear2 (nn.Linear + the fused epilogues) on operand planes. */
+int omt_linear_h(const omt_linear_h_args* args, omt_stream_t stream);
+
+/* LayerNorm as omt_layernorm with plane outputs for the GEMM that consumes it:
+ * y (fp32, may be NULL), (y_hi, y_lo) planes of the normalised row, and optionally (x_hi, x_lo) planes of the RAW
+ * input row -- Attention.forward projects k, v from the un-normalised input (attention.py:407-412).  lds = leading
+ * dimension of every plane (lds % 8 == 0).  The row map applies to x / y; planes are written at the LOGICAL row. */
+int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, uint16_t* y_lo,
+                    uint16_t* x_hi, uint16_t* x_lo, int lds, const float* w, const float* b,
+                    int M, int C, float eps, int seg, int seg_stride, int seg_off, omt_stream_t stream);
+
+/* Tuning knobs (process-wide): "pdl" = 0 (default; measured 2-4 % slower when on) | 1 programmatic dependent launch;
+ * "peg_kernel" = 3 (default) | 4 (cp.async gather + packed f32x2 FMAs; bit-identical);
+ * "attn_kernel" = 3 (default: tcgen05 spatial attention core when N % 128 == 0) | 1 (CUDA-core fp32);
+ * "f16_scheme" = 1 (default: bf16 lo planes, one TMEM accumulator) | 2 (fp16 lo planes scaled by 2^11, cross terms in a
+ * second accumulator) -- every producer and omt_linear_h follow the process-wide value. */
+int omt_set_option(const char* name, int value);
 
 #ifdef __cplusplus
 }

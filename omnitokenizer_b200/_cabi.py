@@ -14,8 +14,24 @@ import torch
 _LIB_NAME = "libomnitok_b200.so"
 _lib = None
 
-EPI_NONE, EPI_GEGLU = 0, 1
-MATH_FP32, MATH_3XTF32, MATH_TF32 = 0, 1, 2
+EPI_NONE, EPI_GEGLU, EPI_QKV = 0, 1, 2
+MATH_FP32, MATH_3XTF32, MATH_F16X3 = 0, 1, 3
+ABI_VERSION = 2
+
+
+class LinearHArgs(ctypes.Structure):
+    """omt_linear_h_args (include/omnitok_b200.h), field for field."""
+    _fields_ = [("a_hi", c_void_p), ("a_lo", c_void_p), ("a2_hi", c_void_p), ("a2_lo", c_void_p), ("n_split", c_int),
+                ("lda", c_int), ("a_seg", c_int), ("a_seg_stride", c_int), ("a_seg_off", c_int),
+                ("w_hi", c_void_p), ("w_lo", c_void_p),
+                ("c", c_void_p), ("ldc", c_int), ("c_seg", c_int), ("c_seg_stride", c_int), ("c_seg_off", c_int),
+                ("u_hi", c_void_p), ("u_lo", c_void_p), ("ldu", c_int),
+                ("M", c_int), ("N", c_int), ("K", c_int),
+                ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int),
+                ("epilogue", c_int),
+                ("q_scale", c_void_p), ("k_scale", c_void_p), ("rope_cos", c_void_p), ("rope_sin", c_void_p),
+                ("qk_cols", c_int), ("tokens", c_int)]
+
 
 # name -> (restype, argtypes); mirrors include/omnitok_b200.h one to one
 SIGNATURES = {
@@ -27,24 +43,26 @@ SIGNATURES = {
                            c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "omt_linear2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "omt_linear_h": (c_int, [POINTER(LinearHArgs), c_void_p]),
     "omt_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int,
                               c_int, c_void_p]),
-    "omt_patchify_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_float, c_void_p]),
+    "omt_layernorm_h": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                c_void_p, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
+    "omt_patchify_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_float, c_void_p]),
     "omt_unpatchify": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "omt_peg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "omt_peg_volume": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "omt_qk_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                             c_int, c_void_p]),
-    "omt_attn_spatial": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
-                                 c_int, c_float, c_void_p]),
-    "omt_attn_window": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
-                                c_int, c_int, c_int, c_int, c_float, c_void_p]),
-    "omt_attn_temporal": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
-                                  c_int, c_int, c_float, c_int, c_void_p]),
+    "omt_attn_spatial": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_int, c_int, c_float, c_void_p]),
+    "omt_attn_window": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "omt_attn_temporal": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "omt_pre_vq": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "omt_vq_search": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "omt_post_vq": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p]),
-    "omt_split_lo": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 
@@ -68,7 +86,7 @@ def load():
         fn = getattr(lib, name)     # AttributeError if a declared symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.omt_abi_version() != 1:
+    if lib.omt_abi_version() != ABI_VERSION:
         raise RuntimeError("libomnitok_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -102,9 +120,21 @@ def call(name: str, *args):
         raise RuntimeError(f"{name} failed ({rc}): {lib.omt_last_error().decode()}")
 
 
+def linear_h(**kw):
+    """omt_linear_h with keyword fields of omt_linear_h_args (tensors -> device pointers; missing fields = 0 / NULL)."""
+    global launch_count
+    lib = load()
+    a = LinearHArgs()
+    for k, v in kw.items():
+        setattr(a, k, _ptr(v) if (v is None or isinstance(v, torch.Tensor)) else v)
+    launch_count += 1
+    rc = lib.omt_linear_h(ctypes.byref(a), _stream())
+    if rc != 0:
+        raise RuntimeError(f"omt_linear_h failed ({rc}): {lib.omt_last_error().decode()}")
+
+
 # process-wide kernel selectors and their library defaults (omt_set_option); tests restore these after flipping them
-DEFAULT_OPTIONS = {"tc_kernel": 2, "tc_block_n": 128, "attn_kernel": 3, "attn_debug": 0, "peg_kernel": 3,
-                   "tc_arrive_cta": 1}
+DEFAULT_OPTIONS = {"attn_kernel": 3, "peg_kernel": 3, "f16_scheme": 1}
 
 
 def set_option(name: str, value: int):

@@ -21,6 +21,7 @@ struct AttnArgs {
   const float* k; int ldk;
   const float* v; int ldv;
   float* o; int ldo;
+  uint16_t* o_hi; uint16_t* o_lo; int scheme;   // optional fp16 hi / bf16 lo operand planes instead of o (ld = ldo)
   const float* bias;   // window: [heads][64][64]
   int N;               // tokens per frame
   int h, w, ws;        // window mode
@@ -169,8 +170,9 @@ __global__ void __launch_bounds__(256, 2) attn_flash_kernel(const AttnArgs a) {
   for (int i = 0; i < 4; ++i) {
     const long long row = token_row<WINDOW>(a, seq, qt * AQ + ty * 4 + i);
     const float inv = 1.0f / lrow[i];
-    *reinterpret_cast<float4*>(a.o + row * a.ldo + head * AD + tx * 4) =
-        make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+    const float4 ov = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+    if (a.o_hi != nullptr) store_split4(a.o_hi, a.o_lo, (size_t)(row * a.ldo + head * AD + tx * 4), ov, a.scheme);
+    else *reinterpret_cast<float4*>(a.o + row * a.ldo + head * AD + tx * 4) = ov;
   }
 }
 
@@ -180,7 +182,8 @@ template <int T>
 __global__ void __launch_bounds__(256) attn_temporal_kernel(const float* __restrict__ q, int ldq,
                                                             const float* __restrict__ k, int ldk,
                                                             const float* __restrict__ v, int ldv,
-                                                            float* __restrict__ o, int ldo, int B,
+                                                            float* __restrict__ o, uint16_t* __restrict__ o_hi,
+                                                            uint16_t* __restrict__ o_lo, int scheme, int ldo, int B,
                                                             int N, int heads, float scale, int causal) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
@@ -226,34 +229,35 @@ __global__ void __launch_bounds__(256) attn_temporal_kernel(const float* __restr
         oy = fmaf(p, vr[j].y, oy);
       }
     }
-    *reinterpret_cast<float2*>(o + row * ldo + col) = make_float2(ox / den, oy / den);
+    const float2 ov = make_float2(ox / den, oy / den);
+    if (o_hi != nullptr) store_split2(o_hi, o_lo, row * ldo + col, ov, scheme);
+    else *reinterpret_cast<float2*>(o + row * ldo + col) = ov;
   }
 }
 
 template <int T>
 static int launch_temporal(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                           float* o, int ldo, int B, int N, int heads, float scale, int causal,
+                           float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, int B, int N, int heads, float scale, int causal,
                            cudaStream_t st) {
   const long long warps = (long long)B * N * heads;
   const unsigned blocks = (unsigned)((warps + 7) / 8);
-  OMT_CUDA(launch_k(attn_temporal_kernel<T>, dim3(blocks), dim3(256), 0, st, q, ldq, k, ldk, v, ldv, o, ldo, B, N, heads, scale, causal));
+  OMT_CUDA(launch_k(attn_temporal_kernel<T>, dim3(blocks), dim3(256), 0, st, q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, g_f16_scheme, ldo, B, N, heads, scale, causal));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
 
-int launch_attn_tc(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo,
-                   int n_seq, int N, int heads, float scale, cudaStream_t st);
-int launch_attn_tc3(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo,
-                    int n_seq, int N, int heads, float scale, cudaStream_t st);
-int g_attn_kernel = 3;   // N % 128 == 0: 3 = tcgen05 3xTF32, Q / P as TMEM operands (attention_tc3.cu);
-                         // 2 = tcgen05 3xTF32, all operands in smem (attention_tc.cu); 1 = CUDA-core fp32
+int launch_attn_tc3(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, uint16_t* o_hi,
+                    uint16_t* o_lo, int ldo, int n_seq, int N, int heads, float scale, cudaStream_t st);
+int g_attn_kernel = 3;   // N % 128 == 0: 3 = tcgen05 3xTF32, Q / P as TMEM operands (attention_tc3.cu); 1 = CUDA-core fp32
 
 static int set_flash_smem() {
-  static bool done = false;
-  if (!done) {
+  static bool done[64];      // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !done[dev]) {
     OMT_CUDA(cudaFuncSetAttribute(attn_flash_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     OMT_CUDA(cudaFuncSetAttribute(attn_flash_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    done = true;
+    done[dev] = true;
   }
   return OMT_OK;
 }
@@ -263,29 +267,28 @@ static int set_flash_smem() {
 using namespace omt;
 
 static int check_attn_ptrs(const char* who, const float* q, int ldq, const float* k, int ldk, const float* v,
-                           int ldv, float* o, int ldo) {
-  OMT_REQUIRE(q && k && v && o, "%s: null pointer", who);
+                           int ldv, float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo) {
+  OMT_REQUIRE(q && k && v && (o || o_hi) && ((o_hi == nullptr) == (o_lo == nullptr)), "%s: null pointer", who);
+  OMT_REQUIRE(((uintptr_t)o_hi | (uintptr_t)o_lo) % 8 == 0, "%s: output planes must be 8-byte aligned", who);
   OMT_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0, "%s: leading dims must be multiples of 4", who);
   OMT_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) % 16 == 0, "%s: pointers must be 16-byte aligned", who);
   return OMT_OK;
 }
 
 extern "C" int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                                float* o, int ldo, int n_seq, int N, int heads, float scale,
+                                float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, int n_seq, int N, int heads, float scale,
                                 omt_stream_t stream) {
   OMT_ENTER();
-  int rc = check_attn_ptrs("omt_attn_spatial", q, ldq, k, ldk, v, ldv, o, ldo);
+  int rc = check_attn_ptrs("omt_attn_spatial", q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, ldo);
   if (rc) return rc;
   OMT_REQUIRE(N > 0 && N % 64 == 0, "omt_attn_spatial: N=%d must be a multiple of 64", N);
   OMT_REQUIRE(heads > 0 && heads <= 65535 && n_seq <= 65535, "omt_attn_spatial: grid too large");
   if (n_seq == 0) return OMT_OK;
   if (g_attn_kernel == 3 && N % 128 == 0)
-    return launch_attn_tc3(q, ldq, k, ldk, v, ldv, o, ldo, n_seq, N, heads, scale, (cudaStream_t)stream);
-  if (g_attn_kernel == 2 && N % 128 == 0)
-    return launch_attn_tc(q, ldq, k, ldk, v, ldv, o, ldo, n_seq, N, heads, scale, (cudaStream_t)stream);
+    return launch_attn_tc3(q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, ldo, n_seq, N, heads, scale, (cudaStream_t)stream);
   rc = set_flash_smem();
   if (rc) return rc;
-  AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, nullptr, N, 0, 0, 0, scale};
+  AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, o_hi, o_lo, g_f16_scheme, nullptr, N, 0, 0, 0, scale};
   dim3 grid(N / AQ, heads, n_seq);
   OMT_CUDA(launch_k(attn_flash_kernel<false>, grid, dim3(256), 65536, (cudaStream_t)stream, a));
   OMT_LAUNCH_CHECK();
@@ -293,10 +296,10 @@ extern "C" int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk
 }
 
 extern "C" int omt_attn_window(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                               float* o, int ldo, const float* bias, int n_frames, int h, int w, int ws,
-                               int heads, float scale, omt_stream_t stream) {
+                               float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, const float* bias, int n_frames, int h,
+                               int w, int ws, int heads, float scale, omt_stream_t stream) {
   OMT_ENTER();
-  int rc = check_attn_ptrs("omt_attn_window", q, ldq, k, ldk, v, ldv, o, ldo);
+  int rc = check_attn_ptrs("omt_attn_window", q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, ldo);
   if (rc) return rc;
   OMT_REQUIRE(bias != nullptr, "omt_attn_window: null bias");
   OMT_REQUIRE(ws * ws == 64, "omt_attn_window: window %dx%d unsupported (8x8 only)", ws, ws);
@@ -306,7 +309,7 @@ extern "C" int omt_attn_window(const float* q, int ldq, const float* k, int ldk,
   if (n_seq == 0) return OMT_OK;
   rc = set_flash_smem();
   if (rc) return rc;
-  AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, bias, h * w, h, w, ws, scale};
+  AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, o_hi, o_lo, g_f16_scheme, bias, h * w, h, w, ws, scale};
   dim3 grid((unsigned)n_seq, heads, 1);
   OMT_CUDA(launch_k(attn_flash_kernel<true>, grid, dim3(256), 65536, (cudaStream_t)stream, a));
   OMT_LAUNCH_CHECK();
@@ -314,15 +317,15 @@ extern "C" int omt_attn_window(const float* q, int ldq, const float* k, int ldk,
 }
 
 extern "C" int omt_attn_temporal(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                                 float* o, int ldo, int B, int T, int N, int heads, float scale, int causal,
-                                 omt_stream_t stream) {
+                                 float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, int B, int T, int N, int heads,
+                                 float scale, int causal, omt_stream_t stream) {
   OMT_ENTER();
-  int rc = check_attn_ptrs("omt_attn_temporal", q, ldq, k, ldk, v, ldv, o, ldo);
+  int rc = check_attn_ptrs("omt_attn_temporal", q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, ldo);
   if (rc) return rc;
   OMT_REQUIRE(T >= 1 && T <= 17, "omt_attn_temporal: T'=%d unsupported (1..17)", T);
   if ((long long)B * N == 0) return OMT_OK;
   cudaStream_t st = (cudaStream_t)stream;
-#define OMT_T_CASE(t) case t: return launch_temporal<t>(q, ldq, k, ldk, v, ldv, o, ldo, B, N, heads, scale, causal, st);
+#define OMT_T_CASE(t) case t: return launch_temporal<t>(q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, ldo, B, N, heads, scale, causal, st);
   switch (T) {
     OMT_T_CASE(1) OMT_T_CASE(2) OMT_T_CASE(3) OMT_T_CASE(4) OMT_T_CASE(5) OMT_T_CASE(6) OMT_T_CASE(7)
     OMT_T_CASE(8) OMT_T_CASE(9) OMT_T_CASE(10) OMT_T_CASE(11) OMT_T_CASE(12) OMT_T_CASE(13) OMT_T_CASE(14)

@@ -39,6 +39,7 @@ constexpr uint32_t IDESC_KK = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(6
 
 struct Args {
   float* o; int ldo;
+  uint16_t* o_hi; uint16_t* o_lo; int scheme;   // optional operand planes instead of o
   int N;
   float scale_log2;
 };
@@ -311,10 +312,13 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     xch[half][r] = l_run;
     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
     const float inv = 1.0f / (l_run + xch[half ^ 1][r]);
-    float* op = a.o + (size_t)(row_q0 + r) * a.ldo + col0 + half * 32;
+    const size_t ooff = (size_t)(row_q0 + r) * a.ldo + col0 + half * 32;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4)
-      *reinterpret_cast<float4*>(op + i) = make_float4(o_acc[i] * inv, o_acc[i + 1] * inv, o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+    for (int i = 0; i < 32; i += 4) {
+      const float4 ov = make_float4(o_acc[i] * inv, o_acc[i + 1] * inv, o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+      if (a.o_hi != nullptr) store_split4(a.o_hi, a.o_lo, ooff + i, ov, a.scheme);
+      else *reinterpret_cast<float4*>(a.o + ooff + i) = ov;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -351,8 +355,8 @@ static int encode2d(CUtensorMap* m, const float* base, int cols, long long rows,
 
 }  // namespace atc3
 
-int launch_attn_tc3(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo,
-                    int n_seq, int N, int heads, float scale, cudaStream_t st) {
+int launch_attn_tc3(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, uint16_t* o_hi,
+                    uint16_t* o_lo, int ldo, int n_seq, int N, int heads, float scale, cudaStream_t st) {
   using namespace atc3;
   CUtensorMap tmQ, tmK, tmV;
   const long long rows = (long long)n_seq * N;
@@ -362,12 +366,14 @@ int launch_attn_tc3(const float* q, int ldq, const float* k, int ldk, const floa
   if (rc) return rc;
   rc = encode2d(&tmV, v, heads * D, rows, ldv, KT);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64];      // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr[dev]) {
     OMT_CUDA(cudaFuncSetAttribute(attn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr = true;
+    attr[dev] = true;
   }
-  Args a{o, ldo, N, scale * 1.4426950408889634f};
+  Args a{o, ldo, o_hi, o_lo, g_f16_scheme, N, scale * 1.4426950408889634f};
   dim3 grid(N / QT, heads, n_seq);
   OMT_CUDA(launch_k(attn_tc3_kernel, grid, dim3(THREADS), SMEM, st, tmQ, tmK, tmV, a));
   OMT_LAUNCH_CHECK();

@@ -144,10 +144,11 @@ static int linear_impl(const QkPrep* qk, const float* A, const float* A2, int n_
     g.qk_cols = qk->qk_cols; g.tokens = qk->tokens;
   }
   if (math == OMT_MATH_FP32) return launch_gemm_fp32(g, epilogue == OMT_EPI_QKV ? OMT_EPI_NONE : epilogue, (cudaStream_t)stream);
-  if (math == OMT_MATH_3XTF32 || math == OMT_MATH_TF32) {
-    OMT_REQUIRE(math == OMT_MATH_TF32 || W_lo != nullptr, "omt_linear: 3xTF32 needs W_lo");
+  if (math == OMT_MATH_3XTF32) {
+    OMT_REQUIRE(W_lo != nullptr, "omt_linear: 3xTF32 needs W_lo");
     return launch_gemm_tc(g, W_lo, epilogue, math, (cudaStream_t)stream, A2, n_split);
   }
+  OMT_REQUIRE(math != OMT_MATH_F16X3, "omt_linear: the f16x3 path takes operand planes (omt_linear_h)");
   set_error("omt_linear: unknown math mode %d", math);
   return OMT_E_ARG;
 }

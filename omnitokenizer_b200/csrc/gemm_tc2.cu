@@ -39,41 +39,6 @@ constexpr int STG_BYTES = EPI_WARPS * 32 * 33 * 4;  // epilogue transpose stagin
 constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024;
 constexpr int THREADS = 192 + EPI_WARPS * 32;   // TMA, MMA, 4 transform warps, 8 epilogue warps
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
-
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// Arrive on a barrier that may live in the peer CTA (cluster-space address).
-// cta_scope = true: default semantics (.release.cta), the form CUTLASS's ClusterBarrier::arrive uses for the 2-SM
-//   pipelines.  What the arrive orders here is this CTA's shared-memory / TMEM traffic (made visible to the async
-//   proxy by the preceding fence.proxy.async / tcgen05.wait::ld); no global memory is published.
-// cta_scope = false: .release.cluster, which ptxas lowers to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR before the arrive --
-//   ncu: 15 % of all stall samples of the FF1 GEMM sit on that sequence in the transform warps, i.e. on the
-//   TMA -> transform -> MMA critical path of every k-block.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr, bool cta_scope) {
-  if (cta_scope)
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-  else
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// W half: data lands in THIS CTA's smem, the transaction bytes are credited to the LEADER's barrier
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
 __device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t"
@@ -101,9 +66,11 @@ template <bool QKV>     // QKV: the epilogue applies rope + l2norm + scale to th
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, const GemmArgs g,
-                const int epilogue, const int num_m_blk, const int num_n_blk, const int n_split, const int arrive_cta) {
+                const int epilogue, const int num_m_blk, const int num_n_blk, const int n_split) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (SW128 operand tiles) by POINTER OFFSET: an integer round trip would lose the shared address
+  // space and turn every staging / transform access into a generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t a_full[STAGES];      // local: this CTA's A stage landed
   __shared__ __align__(8) uint64_t w_full[STAGES];      // used in the leader: both W halves landed
   __shared__ __align__(8) uint64_t ready[STAGES];       // used in the leader: both CTAs' transforms done
@@ -237,7 +204,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&ready[s]), 0), arrive_cta != 0);
+        if (lane == 0) mbar_arrive_remote(mapa(smem_u32(&ready[s]), 0));
       }
     }
   } else {
@@ -390,7 +357,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tmem_empty[acc]), 0), arrive_cta != 0);
+      if (lane == 0) mbar_arrive_remote(mapa(smem_u32(&tmem_empty[acc]), 0));
     }
   }
   // ---- teardown: nobody may leave while the peer can still signal our barriers / read our smem
@@ -428,8 +395,6 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 
 }  // namespace tc2
 
-int g_tc2_arrive_cta = 1;   // omt_set_option("tc_arrive_cta", 0|1): scope of the remote mbarrier arrives (see mbar_arrive_cluster)
-
 int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStream_t st, const float* A2, int n_split) {
   using namespace tc2;
   OMT_REQUIRE(g.K % BK == 0 && g.lda % 4 == 0, "omt_linear(tcgen05 v2): K=%d must be a multiple of 32", g.K);
@@ -462,11 +427,13 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
     rc = encode_map(&tmWlo, W_lo, 2, dims, strides, box);
     if (rc) return rc;
   }
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64];        // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr[dev]) {
     OMT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     OMT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr = true;
+    attr[dev] = true;
   }
   const int num_m_blk = (g.M + 2 * BM - 1) / (2 * BM);
   const int num_n_blk = (g.N + BN - 1) / BN;
@@ -486,10 +453,18 @@ int launch_gemm_tc2(const GemmArgs& g, const float* W_lo, int epilogue, cudaStre
   cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
   const int ns = A2 != nullptr ? n_split : 0x7fffffff;
   if (epilogue == OMT_EPI_QKV)
-    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns, g_tc2_arrive_cta));
+    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<true>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns));
   else
-    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<false>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns, g_tc2_arrive_cta));
+    OMT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<false>, tmA, tmA2, tmW, tmWlo, g, epilogue, num_m_blk, num_n_blk, ns));
   return OMT_OK;
+}
+
+// the tcgen05 3xTF32 kernel applies OMT_EPI_QKV (rope + l2norm + scale) in its own epilogue
+int tc_fuses_qkprep(int math) { return math == OMT_MATH_3XTF32; }
+
+int launch_gemm_tc(const GemmArgs& g, const float* W_lo, int epilogue, int math, cudaStream_t st, const float* A2, int n_split) {
+  OMT_REQUIRE(math == OMT_MATH_3XTF32 && W_lo != nullptr, "omt_linear: the tcgen05 fp32-operand path is 3xTF32 (needs W_lo)");
+  return launch_gemm_tc2(g, W_lo, epilogue, st, A2, n_split);
 }
 
 }  // namespace omt

@@ -47,7 +47,8 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-extern int g_pdl;   // omt_set_option("pdl", 0|1)
+extern int g_pdl;          // omt_set_option("pdl", 0|1)
+extern int g_f16_scheme;   // omt_set_option("f16_scheme", 1|2): format of the lo operand planes (gemm_f16.cu)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -69,6 +70,53 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- fp16 hi / bf16 lo operand split of the f16x3 tensor-core path --------------------------------------------------
+// x ~= hi + lo with hi = fp16(x) (round to nearest, saturating at +-65504) and lo = bf16(x - hi): 11 + 8 significant
+// bits, the same representation error class as the tf32 hi/lo split (2^-21 |x|), but both halves are 16-bit operands
+// of kind::f16 MMAs (2x the tf32 rate, half the operand bytes).  bf16 keeps fp32's exponent range, so lo needs no
+// scaling and the three products  lo.hi + hi.lo + hi.hi  accumulate into ONE fp32 TMEM accumulator.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {   // {low half = a, high half = b}
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t h) {
+  float2 f;
+  asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(h));
+  return f;
+}
+// split two consecutive values: hi2 / lo2 are the packed 32-bit words of the two planes
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = pack_f16x2_sat(a, b);
+  const float2 h = unpack_f16x2(hi2);
+  lo2 = pack_bf16x2(a - h.x, b - h.y);
+}
+// fallback operand format ("f16_scheme" 2): lo = fp16((x - hi) * 2^11), the cross products go to a second accumulator
+__device__ __forceinline__ void split2s(float a, float b, uint32_t& hi2, uint32_t& lo2, int scheme) {
+  hi2 = pack_f16x2_sat(a, b);
+  const float2 h = unpack_f16x2(hi2);
+  lo2 = scheme == 2 ? pack_f16x2_sat((a - h.x) * 2048.0f, (b - h.y) * 2048.0f) : pack_bf16x2(a - h.x, b - h.y);
+}
+// 4 consecutive values -> one 8-byte store per plane
+__device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, size_t off, float4 v, int scheme) {
+  uint2 h, l;
+  split2s(v.x, v.y, h.x, l.x, scheme);
+  split2s(v.z, v.w, h.y, l.y, scheme);
+  *reinterpret_cast<uint2*>(hi + off) = h;
+  *reinterpret_cast<uint2*>(lo + off) = l;
+}
+__device__ __forceinline__ void store_split2(uint16_t* hi, uint16_t* lo, size_t off, float2 v, int scheme) {
+  uint32_t h, l;
+  split2s(v.x, v.y, h, l, scheme);
+  *reinterpret_cast<uint32_t*>(hi + off) = h;
+  *reinterpret_cast<uint32_t*>(lo + off) = l;
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {

@@ -46,12 +46,19 @@ int sm_count() {
 // ------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, whole row in registers (C <= 1024), two-pass statistics.
 // ------------------------------------------------------------------------------------------
+struct LnPlanes {          // optional fp16 hi / bf16 lo operand planes (omt_layernorm_h), written at the LOGICAL row
+  uint16_t* y_hi; uint16_t* y_lo;    // normalised row
+  uint16_t* x_hi; uint16_t* x_lo;    // raw input row (Attention.forward projects k, v from it)
+  int lds; int scheme;
+};
+
 template <int NV>   // float4 chunks per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx,
                                                         float* __restrict__ y, int ldy,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ b, int M, int C,
-                                                        float eps, int seg, int seg_stride, int seg_off) {
+                                                        float eps, int seg, int seg_stride, int seg_off,
+                                                        const LnPlanes pl) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int lrow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -66,6 +73,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (c < C) {
       v[i] = *reinterpret_cast<const float4*>(xr + c);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      if (pl.x_hi != nullptr) store_split4(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i], pl.scheme);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -94,7 +102,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         const float4 bb = *reinterpret_cast<const float4*>(b + c);
         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
       }
-      *reinterpret_cast<float4*>(yr + c) = o;
+      if (y != nullptr) *reinterpret_cast<float4*>(yr + c) = o;
+      if (pl.y_hi != nullptr) store_split4(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, o, pl.scheme);
     }
   }
 }
@@ -105,7 +114,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restrict__ video,
-                                                          float* __restrict__ A,
+                                                          float* __restrict__ A, uint16_t* __restrict__ A_hi,
+                                                          uint16_t* __restrict__ A_lo, const int scheme,
                                                           const float* __restrict__ lw,
                                                           const float* __restrict__ lb, int rows,
                                                           int Cin, int T, int H, int W, int p, int pt,
@@ -141,12 +151,15 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  float* ar = A + (size_t)row * K;
+  const size_t rbase = (size_t)row * K;
   if (lw == nullptr) {        // plain im2col (patch_embed='cnn': the strided Conv3d is a GEMM on raw patch vectors)
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int f = (i * 32 + lane) * 4;
-      if (f < K) *reinterpret_cast<float4*>(ar + f) = v[i];
+      if (f < K) {
+        if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, v[i], scheme);
+        else *reinterpret_cast<float4*>(A + rbase + f) = v[i];
+      }
     }
     return;
   }
@@ -170,7 +183,8 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
       float4 o;
       o.x = v[i].x * rstd * g.x + bb.x; o.y = v[i].y * rstd * g.y + bb.y;
       o.z = v[i].z * rstd * g.z + bb.z; o.w = v[i].w * rstd * g.w + bb.w;
-      *reinterpret_cast<float4*>(ar + f) = o;
+      if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, o, scheme);
+      else *reinterpret_cast<float4*>(A + rbase + f) = o;
     }
   }
 }
@@ -534,20 +548,6 @@ __global__ void __launch_bounds__(256) qk_prep_kernel(float* __restrict__ q, int
   }
 }
 
-__global__ void split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, long long n4) {
-  pdl_sync();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = x[i];
-    float4 o;
-    o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-    o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-    o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-    o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-    lo[i] = o;
-  }
-}
-
 }  // namespace omt
 
 using namespace omt;
@@ -566,33 +566,55 @@ extern "C" int omt_device_info(int* sms, int* major, int* minor) {
   return OMT_OK;
 }
 
-extern "C" int omt_layernorm(const float* x, int ldx, float* y, int ldy, const float* w, const float* b,
-                             int M, int C, float eps, int seg, int seg_stride, int seg_off,
-                             omt_stream_t stream) {
+static int layernorm_impl(const char* who, const float* x, int ldx, float* y, int ldy, const omt::LnPlanes& pl, const float* w,
+                          const float* b, int M, int C, float eps, int seg, int seg_stride, int seg_off, omt_stream_t stream) {
   OMT_ENTER();
-  OMT_REQUIRE(x && y && w, "omt_layernorm: null pointer");
-  OMT_REQUIRE(M >= 0 && C > 0 && C % 4 == 0 && C <= 1024, "omt_layernorm: C=%d must be a multiple of 4, <= 1024", C);
-  OMT_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C, "omt_layernorm: bad leading dims");
+  OMT_REQUIRE(x && w && (y || pl.y_hi), "%s: null pointer", who);
+  OMT_REQUIRE(M >= 0 && C > 0 && C % 4 == 0 && C <= 1024, "%s: C=%d must be a multiple of 4, <= 1024", who, C);
+  OMT_REQUIRE(ldx % 4 == 0 && ldx >= C && (y == nullptr || (ldy % 4 == 0 && ldy >= C)), "%s: bad leading dims", who);
+  OMT_REQUIRE((pl.y_hi == nullptr) == (pl.y_lo == nullptr) && (pl.x_hi == nullptr) == (pl.x_lo == nullptr), "%s: planes come in hi / lo pairs", who);
+  if (pl.y_hi != nullptr || pl.x_hi != nullptr) {
+    OMT_REQUIRE(pl.lds % 4 == 0 && pl.lds >= C, "%s: plane leading dimension %d", who, pl.lds);
+    OMT_REQUIRE(((uintptr_t)pl.y_hi | (uintptr_t)pl.y_lo | (uintptr_t)pl.x_hi | (uintptr_t)pl.x_lo) % 8 == 0, "%s: planes must be 8-byte aligned", who);
+  }
   if (M == 0) return OMT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int nv = (C / 4 + 31) / 32;
   dim3 grid((M + 7) / 8), block(256);
   switch (nv) {
-    case 1: OMT_CUDA(launch_k(layernorm_kernel<1>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
-    case 2: OMT_CUDA(launch_k(layernorm_kernel<2>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
-    case 3: OMT_CUDA(launch_k(layernorm_kernel<3>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
-    case 4: OMT_CUDA(launch_k(layernorm_kernel<4>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
-    default: OMT_CUDA(launch_k(layernorm_kernel<8>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off)); break;
+    case 1: OMT_CUDA(launch_k(layernorm_kernel<1>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
+    case 2: OMT_CUDA(launch_k(layernorm_kernel<2>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
+    case 3: OMT_CUDA(launch_k(layernorm_kernel<3>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
+    case 4: OMT_CUDA(launch_k(layernorm_kernel<4>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
+    default: OMT_CUDA(launch_k(layernorm_kernel<8>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
   }
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
 
-extern "C" int omt_patchify_ln(const float* video, float* A, const float* ln_w, const float* ln_b, int B,
-                               int Cin, int T, int H, int W, int p, int pt, int first, float eps,
-                               omt_stream_t stream) {
+extern "C" int omt_layernorm(const float* x, int ldx, float* y, int ldy, const float* w, const float* b,
+                             int M, int C, float eps, int seg, int seg_stride, int seg_off,
+                             omt_stream_t stream) {
+  OMT_REQUIRE(y != nullptr, "omt_layernorm: null pointer");
+  omt::LnPlanes pl{nullptr, nullptr, nullptr, nullptr, 0, 1};
+  return layernorm_impl("omt_layernorm", x, ldx, y, ldy, pl, w, b, M, C, eps, seg, seg_stride, seg_off, stream);
+}
+
+extern "C" int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, uint16_t* y_lo,
+                               uint16_t* x_hi, uint16_t* x_lo, int lds, const float* w, const float* b,
+                               int M, int C, float eps, int seg, int seg_stride, int seg_off, omt_stream_t stream) {
+  omt::LnPlanes pl{y_hi, y_lo, x_hi, x_lo, lds, omt::g_f16_scheme};
+  return layernorm_impl("omt_layernorm_h", x, ldx, y, ldy, pl, w, b, M, C, eps, seg, seg_stride, seg_off, stream);
+}
+
+extern "C" int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uint16_t* A_lo, const float* ln_w,
+                               const float* ln_b, int B, int Cin, int T, int H, int W, int p, int pt, int first,
+                               float eps, omt_stream_t stream) {
   OMT_ENTER();
-  OMT_REQUIRE(video && A && ((ln_w == nullptr) == (ln_b == nullptr)), "omt_patchify_ln: null pointer");
+  OMT_REQUIRE(video && (A || A_hi) && ((ln_w == nullptr) == (ln_b == nullptr)) && ((A_hi == nullptr) == (A_lo == nullptr)),
+              "omt_patchify_ln: null pointer");
+  OMT_REQUIRE(((uintptr_t)A_hi | (uintptr_t)A_lo) % 8 == 0, "omt_patchify_ln: planes must be 8-byte aligned");
+  const int scheme = omt::g_f16_scheme;
   OMT_REQUIRE(p % 4 == 0 && H % p == 0 && W % p == 0, "omt_patchify_ln: patch %d must be a multiple of 4 dividing %dx%d", p, H, W);
   OMT_REQUIRE(first || (T > 1 && (T - 1) % pt == 0), "omt_patchify_ln: (T-1) %% pt != 0");
   const int PT = first ? 1 : pt;
@@ -604,11 +626,11 @@ extern "C" int omt_patchify_ln(const float* video, float* A, const float* ln_w, 
   dim3 grid((unsigned)((rows + 7) / 8)), block(256);
   const int nv = (K / 4 + 31) / 32;
   if (nv <= 2)
-    OMT_CUDA(launch_k(patchify_ln_kernel<2>, grid, block, 0, st, video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<2>, grid, block, 0, st, video, A, A_hi, A_lo, scheme, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   else if (nv <= 6)
-    OMT_CUDA(launch_k(patchify_ln_kernel<6>, grid, block, 0, st, video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<6>, grid, block, 0, st, video, A, A_hi, A_lo, scheme, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   else
-    OMT_CUDA(launch_k(patchify_ln_kernel<8>, grid, block, 0, st, video, A, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<8>, grid, block, 0, st, video, A, A_hi, A_lo, scheme, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -703,14 +725,26 @@ extern "C" int omt_qk_prep(float* q, int ldq, float* k, int ldk, const float* q_
   return OMT_OK;
 }
 
-extern "C" int omt_split_lo(const float* x, float* lo, int64_t n, omt_stream_t stream) {
-  OMT_ENTER();
-  OMT_REQUIRE(x && lo && n % 4 == 0, "omt_split_lo: n must be a multiple of 4");
-  if (n == 0) return OMT_OK;
-  long long blocks = (n / 4 + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  split_lo_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n / 4);
-  OMT_LAUNCH_CHECK();
-  return OMT_OK;
+namespace omt { extern int g_attn_kernel; }
+
+extern "C" int omt_set_option(const char* name, int value) {
+  if (name == nullptr) return OMT_E_ARG;
+  if (strcmp(name, "pdl") == 0) { omt::g_pdl = value ? 1 : 0; return OMT_OK; }
+  if (strcmp(name, "peg_kernel") == 0) {
+    if (value != 3 && value != 4) { omt::set_error("peg_kernel must be 3 or 4"); return OMT_E_ARG; }
+    omt::g_peg_kernel = value;
+    return OMT_OK;
+  }
+  if (strcmp(name, "attn_kernel") == 0) {
+    if (value != 1 && value != 3) { omt::set_error("attn_kernel must be 1 or 3"); return OMT_E_ARG; }
+    omt::g_attn_kernel = value;
+    return OMT_OK;
+  }
+  if (strcmp(name, "f16_scheme") == 0) {
+    if (value != 1 && value != 2) { omt::set_error("f16_scheme must be 1 or 2"); return OMT_E_ARG; }
+    omt::g_f16_scheme = value;
+    return OMT_OK;
+  }
+  omt::set_error("unknown option %s", name);
+  return OMT_E_ARG;
 }

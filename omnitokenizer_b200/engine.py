@@ -20,18 +20,27 @@ import torch
 from . import _cabi
 from . import layout as L
 
-MATH_MODES = {"fp32": _cabi.MATH_FP32, "3xtf32": _cabi.MATH_3XTF32, "tf32": _cabi.MATH_TF32}
+MATH_MODES = {"fp32": _cabi.MATH_FP32, "3xtf32": _cabi.MATH_3XTF32, "f16x3": _cabi.MATH_F16X3}
+DEFAULT_MATH = "3xtf32"
 
 
 def default_math() -> str:
-    return os.environ.get("OMT_MATH", "3xtf32").lower()
+    return os.environ.get("OMT_MATH", DEFAULT_MATH).lower()
+
+
+class Planes:
+    """fp16 hi / bf16 lo operand planes of an [M, ld] fp32 matrix (the A operands of the f16x3 GEMMs)."""
+
+    def __init__(self, device, M: int, ld: int):
+        self.buf = torch.empty(2, M, ld, device=device, dtype=torch.int16)
+        self.hi, self.lo, self.ld = self.buf[0], self.buf[1], ld
 
 
 class PackedLinear:
     """nn.Linear weight in GEMM layout: rows padded to 128, K padded, optional tf32 hi/lo split."""
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], device, math: int,
-                 k_pad: Optional[int] = None, geglu: Optional[Tuple[int, int]] = None):
+                 k_pad: Optional[int] = None, geglu: Optional[Tuple[int, int]] = None, scheme: int = 1):
         w = weight.detach().to(device=device, dtype=torch.float32)
         if geglu is not None:
             inner, ku = geglu
@@ -40,10 +49,12 @@ class PackedLinear:
         if k_pad is not None:
             w = L.pad_cols(w, k_pad)
         self.k = w.shape[1]
-        w = L.pad_rows(w, 128)
+        w = L.pad_rows(w, 256 if math == _cabi.MATH_F16X3 else 128)
         if math == _cabi.MATH_3XTF32:
             hi = L.tf32_round(w)
             self.w, self.w_lo = hi, (w - hi).contiguous()
+        elif math == _cabi.MATH_F16X3:
+            self.w, self.w_lo = L.split_f16(w, scheme)          # 16-bit operand planes
         else:
             self.w, self.w_lo = w, None
         self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -51,17 +62,21 @@ class PackedLinear:
 
 
 class Workspace:
-    def __init__(self, device, M: int, C: int, ku: int, kmax: int, cd: int):
+    def __init__(self, device, M: int, C: int, ku: int, kmax: int, cd: int, planes: bool):
         f = dict(device=device, dtype=torch.float32)
         self.M = M
         self.buf0 = torch.empty(M, C, **f)
         self.buf1 = torch.empty(M, C, **f)
         self.X, self.Y = self.buf0, self.buf1
-        self.XN = torch.empty(M, C, **f)
         self.QKV = torch.empty(M, 3 * C, **f)
-        self.O = torch.empty(M, C, **f)
-        self.U = torch.empty(M, ku, **f)
         self.P = torch.empty(M, kmax, **f)       # patch matrix (pixels side), rows x K
+        if planes:     # f16x3: every GEMM A operand lives as fp16 hi / bf16 lo planes written by its producer
+            self.XNp, self.XSp, self.Op = Planes(device, M, C), Planes(device, M, C), Planes(device, M, C)
+            self.Up, self.Pp = Planes(device, M, ku), Planes(device, M, kmax)
+        else:
+            self.XN = torch.empty(M, C, **f)
+            self.O = torch.empty(M, C, **f)
+            self.U = torch.empty(M, ku, **f)
         self.z = torch.empty(M, cd, **f)
         self.idx = torch.empty(M, device=device, dtype=torch.int64)
         self.counts = torch.zeros(8192, device=device, dtype=torch.int32)
@@ -82,10 +97,10 @@ class Engine:
     def __init__(self, model, device: torch.device, math: Optional[str] = None):
         _cabi.load()
         _cabi.set_option("pdl", int(os.environ.get("OMT_PDL", "0")))     # programmatic dependent launch between kernels
-        if os.environ.get("OMT_TC_ARRIVE_CTA"):                          # 0 | 1, scope of gemm_tc2's remote mbarrier arrives
-            _cabi.set_option("tc_arrive_cta", int(os.environ["OMT_TC_ARRIVE_CTA"]))
         if os.environ.get("OMT_PEG_KERNEL"):                             # 3 | 4, tuning knob (default: the library's)
             _cabi.set_option("peg_kernel", int(os.environ["OMT_PEG_KERNEL"]))
+        self.scheme = int(os.environ.get("OMT_F16_SCHEME", "1"))         # format of the f16x3 lo planes (see the C header)
+        _cabi.set_option("f16_scheme", self.scheme)
         self.device = device
         self.math_name = (math or default_math()).lower()
         if self.math_name not in MATH_MODES:
@@ -104,6 +119,10 @@ class Engine:
         self.use_vae = bool(model.use_vae)
         self.cd = a.codebook_dim
         self.l2 = bool(a.l2_code)
+        if not self.use_vae and self.cd != 8:
+            raise NotImplementedError(f"--codebook_dim {self.cd}: the VQ search / post_vq kernels are specialised for "
+                                      "codebook_dim 8 (every shipped config); VAE mode takes 8 latent channels as well")
+        self.planes = self.math == _cabi.MATH_F16X3
         if a.attn_dropout != 0 or a.ff_dropout != 0:
             raise NotImplementedError("non-zero dropout reaches SDPA even in eval in the reference (attention.py:451); rejected")
         self._ws: Dict[Tuple, Workspace] = {}
@@ -116,10 +135,13 @@ class Engine:
         dev, m = self.device, self.math
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         self.inner = sd["encoder.enc_spatial_transformer.layers.0.3.4.weight"].shape[1]
-        self.ku = L.round_up(self.inner, 32)
+        self.ku = L.round_up(self.inner, 64 if self.planes else 32)     # K of the second FF GEMM: whole k-blocks
+
+        def PL(weight, bias, **kw):
+            return PackedLinear(weight, bias, dev, m, scheme=self.scheme, **kw)
 
         def lin(name, bias=True, **kw):
-            return PackedLinear(sd[name + ".weight"], sd.get(name + ".bias") if bias else None, dev, m, **kw)
+            return PL(sd[name + ".weight"], sd.get(name + ".bias") if bias else None, **kw)
 
         def t_layer(lp):
             d = {"kind": "t"}
@@ -129,7 +151,7 @@ class Engine:
             d["norm_g"], d["norm_b"] = f32(sd[ap + ".norm.gamma"]), f32(sd[ap + ".norm.beta"])
             d["q_scale"], d["k_scale"] = f32(sd[ap + ".q_scale"]), f32(sd[ap + ".k_scale"])
             # [Wq; Wkv] stacked: one dual-A GEMM writes q | k | v into the QKV buffer
-            d["to_qkv"] = PackedLinear(torch.cat([sd[ap + ".to_q.weight"], sd[ap + ".to_kv.weight"]], dim=0), None, dev, m)
+            d["to_qkv"] = PL(torch.cat([sd[ap + ".to_q.weight"], sd[ap + ".to_kv.weight"]], dim=0), None)
             d["to_out"] = lin(ap + ".to_out", bias=False)
             ff(d, lp + ".3")
             return d
@@ -147,8 +169,8 @@ class Engine:
 
         def ff(d, fp):
             d["ff_g"], d["ff_b"] = f32(sd[fp + ".0.weight"]), f32(sd[fp + ".0.bias"])
-            d["ff1"] = PackedLinear(sd[fp + ".1.weight"], None, dev, m, geglu=(self.inner, self.ku))
-            d["ff2"] = PackedLinear(sd[fp + ".4.weight"], None, dev, m, k_pad=self.ku)
+            d["ff1"] = PL(sd[fp + ".1.weight"], None, geglu=(self.inner, self.ku))
+            d["ff2"] = PL(sd[fp + ".4.weight"], None, k_pad=self.ku)
 
         def transformer(pre, block):
             layers = []
@@ -167,6 +189,7 @@ class Engine:
         self.dec_temporal = transformer("decoder.dec_temporal_transformer", tb)
         self.dec_spatial = transformer("decoder.dec_spatial_transformer", a.dec_block)
 
+        self.has_window = "w" in (a.enc_block + a.dec_block)
         self.pe = {}
         self.cnn = getattr(a, "patch_embed", "linear") == "cnn"
         if self.cnn:
@@ -182,7 +205,7 @@ class Engine:
                 w = sd[pre + ".0.weight"].float().reshape(self.C, -1)                 # (dim, c*pt*p*p)
                 s_, t_ = bn_affine(pre + ".1")
                 self.pe[key] = dict(ln1_g=None, ln1_b=None, ln2_g=None, ln2_b=None,
-                                    lin=PackedLinear(w * s_[:, None], sd[pre + ".0.bias"].float() * s_ + t_, dev, m))
+                                    lin=PL(w * s_[:, None], sd[pre + ".0.bias"].float() * s_ + t_))
             self.px = {}
             for key, pre in (("first", "decoder.to_pixels_first_frame"), ("rest", "decoder.to_pixels")):
                 wt = sd[pre + ".1.weight"].float()                                    # (dim, channels, pt, p, p)
@@ -190,7 +213,7 @@ class Engine:
                 s_, t_ = bn_affine(pre + ".2")
                 w = wt.reshape(self.C, -1).t() * s_.repeat_interleave(per_c)[:, None]  # (channels*pt*p*p, dim)
                 bias = (sd[pre + ".1.bias"].float() * s_ + t_).repeat_interleave(per_c)
-                self.px[key] = PackedLinear(w.contiguous(), bias, dev, m)
+                self.px[key] = PL(w.contiguous(), bias)
         else:
             for key, pre in (("first", "encoder.to_patch_emb_first_frame"), ("rest", "encoder.to_patch_emb")):
                 self.pe[key] = dict(ln1_g=f32(sd[pre + ".1.weight"]), ln1_b=f32(sd[pre + ".1.bias"]), lin=lin(pre + ".2"),
@@ -216,7 +239,7 @@ class Engine:
         ws = self._ws.get(M)
         if ws is None:
             kmax = self.cin * self.pt * self.p * self.p
-            ws = Workspace(self.device, M, self.C, self.ku, kmax, max(self.cd, 16))
+            ws = Workspace(self.device, M, self.C, self.ku, kmax, max(self.cd, 16), self.planes)
             if ws.counts.numel() < self.n_codes:
                 ws.counts = torch.zeros(self.n_codes, device=self.device, dtype=torch.int32)
             while len(self._ws) >= 3:  # keep a few shapes (and their graphs) resident
@@ -234,56 +257,99 @@ class Engine:
 
     def _linear(self, A, lda, lin: PackedLinear, C, ldc, M, *, a_map=(0, 0, 0), c_map=(0, 0, 0), residual=None,
                 ldr=0, epi=_cabi.EPI_NONE, bias=True):
+        """nn.Linear on the fp32-operand paths (CUDA-core fp32 / tcgen05 3xTF32)."""
         _cabi.call("omt_linear", A, lda, a_map[0], a_map[1], a_map[2], lin.w, lin.w_lo, C, ldc, c_map[0], c_map[1],
                    c_map[2], M, lin.n, lin.k, lin.bias if bias else None, residual, ldr, epi, lin.math)
+
+    def _linear_h(self, A: Planes, lin: PackedLinear, M, *, C=None, ldc=0, U: Optional[Planes] = None, A2: Optional[Planes] = None,
+                  n_split=0, a_map=(0, 0, 0), c_map=(0, 0, 0), residual=None, ldr=0, epi=_cabi.EPI_NONE, qk=None):
+        """nn.Linear on operand planes (tcgen05 f16x3).  U: GEGLU output planes; qk: (q_scale, k_scale, cos, sin, qk_cols, tokens)."""
+        kw = dict(a_hi=A.hi, a_lo=A.lo, lda=A.ld, a_seg=a_map[0], a_seg_stride=a_map[1], a_seg_off=a_map[2],
+                  w_hi=lin.w, w_lo=lin.w_lo, c=C, ldc=ldc, c_seg=c_map[0], c_seg_stride=c_map[1], c_seg_off=c_map[2],
+                  M=M, N=lin.n, K=lin.k, bias=lin.bias, residual=residual, ldr=ldr, epilogue=epi)
+        if A2 is not None:
+            kw.update(a2_hi=A2.hi, a2_lo=A2.lo, n_split=n_split)
+        if U is not None:
+            kw.update(u_hi=U.hi, u_lo=U.lo, ldu=U.ld)
+        if qk is not None:
+            kw.update(q_scale=qk[0], k_scale=qk[1], rope_cos=qk[2], rope_sin=qk[3], qk_cols=qk[4], tokens=qk[5])
+        _cabi.linear_h(**kw)
 
     def _ln(self, x, y, g, b, M, C=None, seg=(0, 0, 0)):
         C = C or self.C
         _cabi.call("omt_layernorm", x, C, y, C, g, b, M, C, 1e-5, seg[0], seg[1], seg[2])
 
+    def _ln_h(self, x, yp: Planes, g, b, M, xp: Optional[Planes] = None):
+        """LayerNorm straight into the operand planes of the consuming GEMM (+ planes of the raw row for to_kv)."""
+        C = self.C
+        _cabi.call("omt_layernorm_h", x, C, None, 0, yp.hi, yp.lo, None if xp is None else xp.hi,
+                   None if xp is None else xp.lo, yp.ld, g, b, M, C, 1e-5, 0, 0, 0)
+
     # ------------------------------------------------------------------ transformer
-    def _transformer(self, tr, ws: Workspace, B, T, h, w, temporal: bool):
+    def _transformer(self, tr, ws: Workspace, B, T, h, w, temporal: bool, out_planes: Optional[Planes] = None):
+        """modules/attention.py:655-689.  out_planes: norm_out goes to operand planes (decoder -> to_pixels GEMMs)."""
         C, N, M = self.C, h * w, ws.M
+        H = self.planes
         q_ptr = ws.QKV.data_ptr()
         k_ptr, v_ptr = q_ptr + C * 4, q_ptr + 2 * C * 4
         ld3 = 3 * C
+        o, o_hi, o_lo = (None, ws.Op.hi, ws.Op.lo) if H else (ws.O, None, None)
         for lyr in tr["layers"]:
             if lyr["kind"] == "t":
                 _cabi.call("omt_peg_volume", ws.X, ws.Y, lyr["peg_w"], lyr["peg_b"], B, T, h, w, C, int(temporal),
                            int(self.causal_peg))
                 ws.X, ws.Y = ws.Y, ws.X
-                self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
-                # q from the normalised input, k / v from the RAW input (attention.py:407-412), one launch
+                # q from the normalised input, k / v from the RAW input (attention.py:407-412), one launch;
                 # rope (spatial blocks) + l2norm + q/k scale ride in the same launch (fused GEMM epilogue)
                 wq = lyr["to_qkv"]
                 cos = sin = None
                 if (not temporal) and self.rope:
                     cos, sin = self._table(("rope", N), lambda: L.rope_tables(N, self.dh))
-                if self.fuse_qkprep(M):
-                    _cabi.call("omt_linear2", ws.XN, ws.X, C, C, wq.w, wq.w_lo, q_ptr, ld3, M, wq.n, wq.k, wq.math,
-                               lyr["q_scale"], lyr["k_scale"], cos, sin, 2 * C, N)
+                if H:
+                    self._ln_h(ws.X, ws.XNp, lyr["norm_g"], lyr["norm_b"], M, xp=ws.XSp)
+                    self._linear_h(ws.XNp, wq, M, C=q_ptr, ldc=ld3, A2=ws.XSp, n_split=C, epi=_cabi.EPI_QKV,
+                                   qk=(lyr["q_scale"], lyr["k_scale"], cos, sin, 2 * C, N))
                 else:
-                    _cabi.call("omt_linear2", ws.XN, ws.X, C, C, wq.w, wq.w_lo, q_ptr, ld3, M, wq.n, wq.k, wq.math,
-                               None, None, None, None, 0, 0)
-                    _cabi.call("omt_qk_prep", q_ptr, ld3, k_ptr, ld3, lyr["q_scale"], lyr["k_scale"], cos, sin, M, N,
-                               self.heads)
+                    self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
+                    if self.fuse_qkprep(M):
+                        _cabi.call("omt_linear2", ws.XN, ws.X, C, C, wq.w, wq.w_lo, q_ptr, ld3, M, wq.n, wq.k, wq.math,
+                                   lyr["q_scale"], lyr["k_scale"], cos, sin, 2 * C, N)
+                    else:
+                        _cabi.call("omt_linear2", ws.XN, ws.X, C, C, wq.w, wq.w_lo, q_ptr, ld3, M, wq.n, wq.k, wq.math,
+                                   None, None, None, None, 0, 0)
+                        _cabi.call("omt_qk_prep", q_ptr, ld3, k_ptr, ld3, lyr["q_scale"], lyr["k_scale"], cos, sin, M, N,
+                                   self.heads)
                 if temporal:
-                    _cabi.call("omt_attn_temporal", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, ws.O, C, B, T, N, self.heads,
-                               8.0, int(self.causal_attn))
+                    _cabi.call("omt_attn_temporal", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, o, o_hi, o_lo, C, B, T, N,
+                               self.heads, 8.0, int(self.causal_attn))
                 else:
-                    _cabi.call("omt_attn_spatial", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, ws.O, C, B * T, N, self.heads,
-                               8.0)
-                self._linear(ws.O, C, lyr["to_out"], ws.X, C, M, residual=ws.X, ldr=C)
+                    _cabi.call("omt_attn_spatial", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, o, o_hi, o_lo, C, B * T, N,
+                               self.heads, 8.0)
+                proj = lyr["to_out"]
             else:
-                self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
-                self._linear(ws.XN, C, lyr["qkv"], q_ptr, ld3, M)
-                _cabi.call("omt_attn_window", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, ws.O, C, lyr["bias"], B * T, h, w,
-                           self.ws, self.heads, float(self.dh) ** -0.5)
-                self._linear(ws.O, C, lyr["proj"], ws.X, C, M, residual=ws.X, ldr=C)
-            self._ln(ws.X, ws.XN, lyr["ff_g"], lyr["ff_b"], M)
-            self._linear(ws.XN, C, lyr["ff1"], ws.U, self.ku, M, epi=_cabi.EPI_GEGLU)
-            self._linear(ws.U, self.ku, lyr["ff2"], ws.X, C, M, residual=ws.X, ldr=C)
-        self._ln(ws.X, ws.X, tr["out_g"], tr["out_b"], M)
+                if H:
+                    self._ln_h(ws.X, ws.XNp, lyr["norm_g"], lyr["norm_b"], M)
+                    self._linear_h(ws.XNp, lyr["qkv"], M, C=q_ptr, ldc=ld3)
+                else:
+                    self._ln(ws.X, ws.XN, lyr["norm_g"], lyr["norm_b"], M)
+                    self._linear(ws.XN, C, lyr["qkv"], q_ptr, ld3, M)
+                _cabi.call("omt_attn_window", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, o, o_hi, o_lo, C, lyr["bias"], B * T, h,
+                           w, self.ws, self.heads, float(self.dh) ** -0.5)
+                proj = lyr["proj"]
+            if H:
+                self._linear_h(ws.Op, proj, M, C=ws.X, ldc=C, residual=ws.X, ldr=C)
+                self._ln_h(ws.X, ws.XNp, lyr["ff_g"], lyr["ff_b"], M)
+                self._linear_h(ws.XNp, lyr["ff1"], M, U=ws.Up, epi=_cabi.EPI_GEGLU)
+                self._linear_h(ws.Up, lyr["ff2"], M, C=ws.X, ldc=C, residual=ws.X, ldr=C)
+            else:
+                self._linear(ws.O, C, proj, ws.X, C, M, residual=ws.X, ldr=C)
+                self._ln(ws.X, ws.XN, lyr["ff_g"], lyr["ff_b"], M)
+                self._linear(ws.XN, C, lyr["ff1"], ws.U, self.ku, M, epi=_cabi.EPI_GEGLU)
+                self._linear(ws.U, self.ku, lyr["ff2"], ws.X, C, M, residual=ws.X, ldr=C)
+        if out_planes is not None:
+            self._ln_h(ws.X, out_planes, tr["out_g"], tr["out_b"], M)
+        else:
+            self._ln(ws.X, ws.X, tr["out_g"], tr["out_b"], M)
 
     # ------------------------------------------------------------------ shapes / graphs
     def _shape(self, shape):
@@ -292,8 +358,13 @@ class Engine:
             raise ValueError(f"expected {self.cin} channels, got {Cin}")
         assert (T - 1) % self.pt == 0, (f"number of frames ({T}) minus one ({T - 1}) must be divisible by temporal "
                                         f"patch size ({self.pt})")
-        if H != W or H % (self.p * self.ws) != 0:
-            raise ValueError(f"frames must be square with side a multiple of {self.p * self.ws} (got {H}x{W})")
+        if H != W or H % self.p != 0:
+            raise ValueError(f"frames must be square with side a multiple of the patch size {self.p} (got {H}x{W})")
+        if self.has_window and (self.ws * self.ws != 64 or (H // self.p) % self.ws != 0):
+            raise ValueError(f"window blocks need twod_window_size 8 and a token grid divisible by it (got window "
+                             f"{self.ws}, grid {H // self.p}x{W // self.p}): omt_attn_window is specialised for 8x8 windows")
+        if ((H // self.p) * (W // self.p)) % 64 != 0:
+            raise ValueError(f"tokens per frame ({(H // self.p) * (W // self.p)}) must be a multiple of 64 (attention tiles)")
         return B, T, H, W, 1 + (T - 1) // self.pt, H // self.p, W // self.p
 
     @staticmethod
@@ -328,23 +399,25 @@ class Engine:
         B, T, H, W, Tp, h, w = dims
         N, C = h * w, self.C
         ws.reset()
-        pe = self.pe["first"]
         k1 = self.cin * self.p * self.p
-        _cabi.call("omt_patchify_ln", x, ws.P, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p, self.pt, 1, 1e-5)
-        cmap = (N, Tp * N, 0)
-        self._linear(ws.P, k1, pe["lin"], ws.X, C, B * N, c_map=cmap)
-        if not self.cnn:
-            self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], B * N, seg=cmap)
-        if Tp > 1:
-            pe = self.pe["rest"]
-            k2 = k1 * self.pt
-            rows = B * (Tp - 1) * N
-            _cabi.call("omt_patchify_ln", x, ws.P, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p, self.pt, 0,
-                       1e-5)
-            cmap = ((Tp - 1) * N, Tp * N, N)
-            self._linear(ws.P, k2, pe["lin"], ws.X, C, rows, c_map=cmap)
+
+        def embed(pe, first, rows, K, cmap):
+            if self.planes:
+                Pp = Planes.__new__(Planes)          # dense [rows, K] view at the start of the patch planes
+                Pp.hi, Pp.lo, Pp.ld = ws.Pp.hi, ws.Pp.lo, K
+                _cabi.call("omt_patchify_ln", x, None, Pp.hi, Pp.lo, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p,
+                           self.pt, first, 1e-5)
+                self._linear_h(Pp, pe["lin"], rows, C=ws.X, ldc=C, c_map=cmap)
+            else:
+                _cabi.call("omt_patchify_ln", x, ws.P, None, None, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p,
+                           self.pt, first, 1e-5)
+                self._linear(ws.P, K, pe["lin"], ws.X, C, rows, c_map=cmap)
             if not self.cnn:
                 self._ln(ws.X, ws.X, pe["ln2_g"], pe["ln2_b"], rows, seg=cmap)
+
+        embed(self.pe["first"], 1, B * N, k1, (N, Tp * N, 0))
+        if Tp > 1:
+            embed(self.pe["rest"], 0, B * (Tp - 1) * N, k1 * self.pt, ((Tp - 1) * N, Tp * N, N))
         self._transformer(self.enc_spatial, ws, B, Tp, h, w, temporal=False)
         self._transformer(self.enc_temporal, ws, B, Tp, h, w, temporal=True)
         cd = self.pre_w.shape[0]
@@ -395,16 +468,21 @@ class Engine:
             _cabi.call("omt_post_vq", None, None, self._dense(ws.zc_in, M, cdp), None, None, self.post_w, self.post_b,
                        ws.X, M, C, cdp)
         self._transformer(self.dec_temporal, ws, B, Tp, h, w, temporal=True)
-        self._transformer(self.dec_spatial, ws, B, Tp, h, w, temporal=False)
+        self._transformer(self.dec_spatial, ws, B, Tp, h, w, temporal=False, out_planes=ws.XNp if self.planes else None)
         T = 1 + (Tp - 1) * self.pt
         H, W = h * self.p, w * self.p
         k1 = self.cin * self.p * self.p
-        self._linear(ws.X, C, self.px["first"], ws.P, k1, B * N, a_map=(N, Tp * N, 0))
-        _cabi.call("omt_unpatchify", ws.P, ws.video, B, self.cin, T, H, W, self.p, self.pt, 1)
+
+        def pixels(px, first, rows, K, amap):
+            if self.planes:
+                self._linear_h(ws.XNp, px, rows, C=ws.P, ldc=K, a_map=amap)
+            else:
+                self._linear(ws.X, C, px, ws.P, K, rows, a_map=amap)
+            _cabi.call("omt_unpatchify", ws.P, ws.video, B, self.cin, T, H, W, self.p, self.pt, first)
+
+        pixels(self.px["first"], 1, B * N, k1, (N, Tp * N, 0))
         if Tp > 1:
-            k2 = k1 * self.pt
-            self._linear(ws.X, C, self.px["rest"], ws.P, k2, B * (Tp - 1) * N, a_map=((Tp - 1) * N, Tp * N, N))
-            _cabi.call("omt_unpatchify", ws.P, ws.video, B, self.cin, T, H, W, self.p, self.pt, 0)
+            pixels(self.px["rest"], 0, B * (Tp - 1) * N, k1 * self.pt, ((Tp - 1) * N, Tp * N, N))
 
     def decode(self, dims, *, idx=None, zc=None, straight_through=False) -> torch.Tensor:
         """dims (B,T',h,w).  idx: int64 [M] codes | zc: fp32 [M, cd] latents (VAE).  With straight_through

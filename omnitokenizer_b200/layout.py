@@ -72,6 +72,16 @@ def tf32_round(w: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & -8192).view(torch.float32)
 
 
+def split_f16(w: torch.Tensor, scheme: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Operand planes of the f16x3 tensor-core path (csrc/omt_common.cuh): hi = fp16(w) (round to nearest, saturating)
+    and lo = bf16(w - hi); scheme 2: lo = fp16((w - hi) * 2^11).  Same rounding as the device-side split."""
+    w = w.float()
+    hi = w.clamp(-65504.0, 65504.0).to(torch.float16)
+    r = w - hi.float()
+    lo = r.to(torch.bfloat16) if scheme == 1 else (r * 2048.0).clamp(-65504.0, 65504.0).to(torch.float16)
+    return hi.contiguous(), lo.contiguous()
+
+
 def pad_rows(w: torch.Tensor, mult: int) -> torch.Tensor:
     n = w.shape[0]
     n_pad = (n + mult - 1) // mult * mult

@@ -296,16 +296,44 @@ class OmniTokenizer_VQGAN(nn.Module):
         self.engine()
         return self
 
+    def _track_usage(self, counts, M):
+        """Eval-time side effects of Codebook.forward (modules/codebook.py:122-140): batch usage from the fixed-size
+        histogram the search kernel filled (replaces torch.unique, no host sync), EMA of codebook_usage, call_cnt."""
+        cb = self.codebook
+        usage = counts[:cb.n_codes].float() / M
+        if cb.call_cnt == 0:
+            cb.codebook_usage.data = usage
+        else:
+            cb.codebook_usage.data = cb.usage_sigma * cb.codebook_usage.data + (1 - cb.usage_sigma) * usage
+        cb.call_cnt += 1
+        return usage
+
+    def _empty_encode(self, x, is_image, include_embeddings):
+        """B == 0 (a surplus rank of a batch-sharded run): right-shaped empty results, no kernel launch."""
+        a = self.args
+        T = 1 if is_image else x.shape[2]
+        Tp, h, w = 1 + (T - 1) // a.temporal_patch_size, x.shape[-2] // a.patch_size, x.shape[-1] // a.patch_size
+        if self.use_vae:
+            shape = (0, a.codebook_dim, h, w) if is_image else (0, a.codebook_dim, Tp, h, w)
+            return torch.empty(shape, device=self.device)
+        enc = torch.empty((0, Tp, h, w), dtype=torch.int64, device=self.device)
+        if include_embeddings:
+            return torch.empty((0, a.codebook_dim, Tp, h, w), device=self.device), enc
+        return enc
+
     # ---------------------------------------------------------------- the hot path
     @torch.no_grad()
     def encode(self, x, is_image, include_embeddings=False):
         """omnitokenizer.py:247-266."""
         eng = self.engine()
+        if x.shape[0] == 0:
+            return self._empty_encode(x, is_image, include_embeddings)
         with torch.cuda.device(self.device):
             xv = x.unsqueeze(2) if is_image else x
             ws, (B, Tp, h, w) = eng.encode(xv.float(), "raw" if self.use_vae else "vq")
             if not self.use_vae:
                 enc = ws.idx.view(B, Tp, h, w).clone()
+                self._track_usage(ws.counts, ws.M)             # Codebook.forward runs inside encode() too
                 if include_embeddings:
                     z = eng.z_view(ws)
                     e = eng.E[ws.idx]
@@ -345,6 +373,13 @@ class OmniTokenizer_VQGAN(nn.Module):
                     B, Tp, h, w = enc.shape
                 self._check_cnn_grid(h, w)
                 idx = enc.reshape(-1).to(device=self.device, dtype=torch.int64)
+                if B == 0:
+                    T = 1 + (Tp - 1) * self.args.temporal_patch_size
+                    video = torch.empty((0, self.args.image_channels, T, h * self.patch_size, w * self.patch_size), device=self.device)
+                    return video.squeeze(2) if is_image else video
+                # F.embedding device-asserts on out-of-range indices (omnitokenizer.py:270); same here, without a host sync
+                torch._assert_async(((idx >= 0) & (idx < self.codebook.n_codes)).all(),
+                                    "decode: code index out of range [0, n_codes)")
                 video = eng.decode((B, Tp, h, w), idx=idx)
             else:
                 z = encodings.to(device=self.device, dtype=torch.float32)
@@ -388,15 +423,10 @@ class OmniTokenizer_VQGAN(nn.Module):
                 zq = eng.zq_view(ws).clone()
                 cb = self.codebook
                 n_codes = cb.n_codes
-                usage = counts[:n_codes].float() / M                                  # codebook.py:54-72 (fixed-size histogram)
+                usage = self._track_usage(counts, M)                                  # codebook.py:54-72, 133-138
                 e = eng.E[idx]
                 commitment = 0.25 * torch.mean((z - e) ** 2)                           # codebook.py:93
                 perplexity = torch.exp(-torch.sum(usage * torch.log(usage + 1e-10)))   # codebook.py:122-123
-                if cb.call_cnt == 0:                                                  # codebook.py:133-138
-                    cb.codebook_usage.data = usage
-                else:
-                    cb.codebook_usage.data = cb.usage_sigma * cb.codebook_usage.data + (1 - cb.usage_sigma) * usage
-                cb.call_cnt += 1
                 avg_usage = (cb.codebook_usage.data > (1 / n_codes)).sum() / n_codes
                 vq_output = dict(embeddings=zq.view(B, Tp, h, w, -1).permute(0, 4, 1, 2, 3).contiguous(),
                                  encodings=idx.view(B, Tp, h, w), commitment_loss=commitment, perplexity=perplexity,

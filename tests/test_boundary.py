@@ -95,8 +95,8 @@ def test_cabi_exports_every_declared_symbol():
     lib = _cabi.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.omt_abi_version() == 1
-    assert int(re.search(r"#define OMT_ABI_VERSION (\d+)", hdr).group(1)) == 1
+    assert lib.omt_abi_version() == _cabi.ABI_VERSION == 2
+    assert int(re.search(r"#define OMT_ABI_VERSION (\d+)", hdr).group(1)) == _cabi.ABI_VERSION
 
 
 def test_no_cpu_fallback():

@@ -1,0 +1,226 @@
+"""GPU op-level parity of the f16x3 path: the kind::f16 GEMM on fp16 hi / bf16 lo operand planes (omt_linear_h) and
+every producer that writes planes (LayerNorm, patch gather, the three attention cores, the GEGLU epilogue), against
+fp64 torch on the same inputs.  Tolerance: fp32 round-off class (2e-5 on |A.W| ~ 1), the same bar as 3xTF32."""
+
+import os
+
+import pytest
+import torch
+
+from oracle import omni_oracle as oo
+
+pytestmark = pytest.mark.gpu
+
+SCHEMES = [int(v) for v in os.environ.get("OMT_TEST_SCHEMES", "1,2").split(",") if v]
+
+
+def _cabi(scheme=1):
+    from omnitokenizer_b200 import _cabi
+    _cabi.load()
+    _cabi.set_option("f16_scheme", scheme)
+    return _cabi
+
+
+def _rand(shape, seed, scale=1.0):
+    return (torch.rand(shape, generator=torch.Generator().manual_seed(seed)) - 0.5) * 2 * scale
+
+
+def _planes(t, dev, scheme, pad_rows=0):
+    from omnitokenizer_b200 import layout as L
+    if pad_rows:
+        t = L.pad_rows(t, pad_rows)
+    hi, lo = L.split_f16(t, scheme)
+    return hi.to(dev), lo.to(dev)
+
+
+def _join(hi, lo, scheme):
+    """fp32 value the planes stand for."""
+    hi, lo = hi.cpu(), lo.cpu()
+    if scheme == 1:
+        return hi.view(torch.float16).float() + lo.view(torch.bfloat16).float()
+    return hi.view(torch.float16).float() + lo.view(torch.float16).float() / 2048.0
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("M,N,K", [(64, 512, 512), (320, 192, 512), (1024, 1024, 768), (4160, 2816, 512), (192, 512, 192)])
+def test_linear_h_plain_bias_residual(cuda, M, N, K, scheme):
+    cabi = _cabi(scheme)
+    A, Wt, b, R = _rand((M, K), 1), _rand((N, K), 2, 0.05), _rand((N,), 3), _rand((M, N), 4)
+    ref = (A.double() @ Wt.double().t() + b.double() + R.double()).float()
+    ah, al = _planes(A, cuda, scheme)
+    wh, wl = _planes(Wt, cuda, scheme, 256)
+    out = torch.full((M, N), float("nan"), device=cuda)
+    cabi.linear_h(a_hi=ah, a_lo=al, lda=K, w_hi=wh, w_lo=wl, c=out, ldc=N, M=M, N=N, K=K, bias=b.to(cuda),
+                  residual=R.to(cuda), ldr=N, epilogue=cabi.EPI_NONE)
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 2e-5, f"f16x3 scheme {scheme} M{M} N{N} K{K}: max err {err:.3e}"
+    # in-place residual (C aliases the residual, as every out-projection / FF2 call does)
+    X = R.to(cuda).clone()
+    cabi.linear_h(a_hi=ah, a_lo=al, lda=K, w_hi=wh, w_lo=wl, c=X, ldc=N, M=M, N=N, K=K, bias=b.to(cuda), residual=X,
+                  ldr=N, epilogue=cabi.EPI_NONE)
+    assert torch.equal(X, out)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_linear_h_geglu_and_rowmaps(cuda, scheme):
+    cabi = _cabi(scheme)
+    from omnitokenizer_b200 import layout as L
+    M, K, inner = 320, 512, 1365
+    ku = L.round_up(inner, 64)
+    A, W1 = _rand((M, K), 5), _rand((2 * inner, K), 6, 0.05)
+    y = A.double() @ W1.double().t()
+    ref = (oo.gelu_erf(y[:, inner:]) * y[:, :inner]).float()
+    ah, al = _planes(A, cuda, scheme)
+    wh, wl = _planes(L.pack_geglu(W1, inner, ku), cuda, scheme, 256)
+    U = torch.full((2, M, ku), -1, dtype=torch.int16, device=cuda)
+    cabi.linear_h(a_hi=ah, a_lo=al, lda=K, w_hi=wh, w_lo=wl, u_hi=U[0], u_lo=U[1], ldu=ku, M=M, N=2 * ku, K=K,
+                  epilogue=cabi.EPI_GEGLU)
+    torch.cuda.synchronize()
+    got = _join(U[0], U[1], scheme)
+    assert (got[:, :inner] - ref).abs().max().item() < 2e-5
+    assert torch.count_nonzero(U[:, :, inner:]).item() == 0          # zero padding columns are exact zeros in both planes
+    # second FF GEMM straight from the planes (K = ku, zero-padded)
+    W2 = _rand((512, inner), 16, 0.05)
+    w2h, w2l = _planes(L.pad_cols(W2, ku), cuda, scheme, 256)
+    X = torch.empty(M, 512, device=cuda)
+    cabi.linear_h(a_hi=U[0], a_lo=U[1], lda=ku, w_hi=w2h, w_lo=w2l, c=X, ldc=512, M=M, N=512, K=ku, epilogue=cabi.EPI_NONE)
+    assert (X.cpu() - (ref.double() @ W2.double().t()).float()).abs().max().item() < 2e-5
+    # row maps: logical rows gather from / scatter into the canonical buffer (first-frame / rest-frames)
+    B, T, N, Kp = 2, 3, 64, 192
+    Xc = _rand((B * T * N, 512), 7)
+    xh, xl = _planes(Xc, cuda, scheme)
+    Wt = _rand((Kp, 512), 8, 0.05)
+    wqh, wql = _planes(Wt, cuda, scheme, 256)
+    rows = B * (T - 1) * N
+    P = torch.full((rows, Kp), float("nan"), device=cuda)
+    cabi.linear_h(a_hi=xh, a_lo=xl, lda=512, a_seg=(T - 1) * N, a_seg_stride=T * N, a_seg_off=N, w_hi=wqh, w_lo=wql,
+                  c=P, ldc=Kp, M=rows, N=Kp, K=512, epilogue=cabi.EPI_NONE)
+    sel = Xc.view(B, T, N, 512)[:, 1:].reshape(rows, 512)
+    assert (P.cpu() - (sel.double() @ Wt.double().t()).float()).abs().max().item() < 2e-5
+    Xo = torch.zeros(B * T * N, 512, device=cuda)
+    Wb = _rand((512, Kp), 9, 0.05)
+    wbh, wbl = _planes(Wb, cuda, scheme, 256)
+    ph, pl = _planes(P.cpu(), cuda, scheme)
+    cabi.linear_h(a_hi=ph, a_lo=pl, lda=Kp, w_hi=wbh, w_lo=wbl, c=Xo, ldc=512, c_seg=(T - 1) * N, c_seg_stride=T * N,
+                  c_seg_off=N, M=rows, N=512, K=Kp, epilogue=cabi.EPI_NONE)
+    want = torch.zeros(B, T, N, 512)
+    want[:, 1:] = (P.cpu().double() @ Wb.double().t()).float().view(B, T - 1, N, 512)
+    assert (Xo.cpu().view(B, T, N, 512) - want).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_linear_h_dual_a_qkv(cuda, scheme):
+    """q from LN(x), k/v from raw x in one launch (attention.py:407-412), rope + l2norm + scale in the epilogue."""
+    cabi = _cabi(scheme)
+    from omnitokenizer_b200 import layout as L
+    M, K, N = 640, 512, 128
+    A1, A2, Wt = _rand((M, K), 70), _rand((M, K), 71), _rand((1536, K), 72, 0.05)
+    ref = torch.cat([A1.double() @ Wt[:512].double().t(), A2.double() @ Wt[512:].double().t()], dim=1).float()
+    a1h, a1l = _planes(A1, cuda, scheme)
+    a2h, a2l = _planes(A2, cuda, scheme)
+    wh, wl = _planes(Wt, cuda, scheme, 256)
+    qs, ks = _rand((64,), 73, 0.5) + 1.0, _rand((64,), 74, 0.5) + 1.0
+    cos, sin = L.rope_tables(N, 64)
+    out = torch.empty(M, 1536, device=cuda)
+    for tables in ((cos, sin), (None, None)):
+        out.fill_(float("nan"))
+        cabi.linear_h(a_hi=a1h, a_lo=a1l, a2_hi=a2h, a2_lo=a2l, n_split=512, lda=K, w_hi=wh, w_lo=wl, c=out, ldc=1536,
+                      M=M, N=1536, K=K, epilogue=cabi.EPI_QKV, q_scale=qs.to(cuda), k_scale=ks.to(cuda),
+                      rope_cos=None if tables[0] is None else tables[0].to(cuda),
+                      rope_sin=None if tables[1] is None else tables[1].to(cuda), qk_cols=1024, tokens=N)
+        got = out.cpu()
+        for sl, sc in ((slice(0, 512), qs), (slice(512, 1024), ks)):
+            t = ref[:, sl].reshape(M // N, N, 8, 64)
+            if tables[0] is not None:
+                t = oo.apply_rope(t, cos, sin)
+            want = (oo.l2norm(t) * sc).reshape(M, 512)
+            assert (got[:, sl] - want).abs().max().item() < 2e-5
+        assert (got[:, 1024:] - ref[:, 1024:]).abs().max().item() < 2e-5
+    # plain dual-A form too (window qkv uses the plain epilogue)
+    out.fill_(float("nan"))
+    cabi.linear_h(a_hi=a1h, a_lo=a1l, a2_hi=a2h, a2_lo=a2l, n_split=512, lda=K, w_hi=wh, w_lo=wl, c=out, ldc=1536,
+                  M=M, N=1536, K=K, epilogue=cabi.EPI_NONE)
+    assert (out.cpu() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(20480, 1024, 1408), (5120, 512, 512), (40960, 512, 512)])
+def test_linear_h_multiwave_deterministic(cuda, M, N, K):
+    """Several waves of tiles per cluster (accumulator double-buffering, slab reuse, TMA-store ordering): the same bits
+    run after run, and the first / last rows are right."""
+    cabi = _cabi(1)
+    from omnitokenizer_b200 import layout as L
+    A = (torch.rand((M, K), device=cuda, generator=torch.Generator(device=cuda).manual_seed(31)) - 0.5)
+    W = (torch.rand((N, K), device=cuda, generator=torch.Generator(device=cuda).manual_seed(32)) - 0.5) * 0.05
+    R = (torch.rand((M, N), device=cuda, generator=torch.Generator(device=cuda).manual_seed(33)) - 0.5)
+    ah, al = L.split_f16(A)
+    wh, wl = L.split_f16(L.pad_rows(W, 256))
+    outs = []
+    for _ in range(4):
+        out = torch.full((M, N), float("nan"), device=cuda)
+        cabi.linear_h(a_hi=ah, a_lo=al, lda=K, w_hi=wh, w_lo=wl, c=out, ldc=N, M=M, N=N, K=K, residual=R, ldr=N,
+                      epilogue=cabi.EPI_NONE)
+        outs.append(out)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    for sl in (slice(0, 256), slice(M - 256, M)):
+        ref = (A[sl].double() @ W.double().t() + R[sl].double()).float()
+        assert (outs[0][sl] - ref).abs().max().item() < 2e-5
+    assert not torch.isnan(outs[0]).any()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_plane_producers(cuda, scheme):
+    """LayerNorm (+ raw-row planes), patch gather and the attention cores write planes that stand for the same fp32 values
+    their fp32 forms produce (within the split's 2^-20 relative representation error)."""
+    cabi = _cabi(scheme)
+    M = 320
+    x = _rand((M, 512), 10, 3.0)
+    g, b = _rand((512,), 11) + 1.0, _rand((512,), 12)
+    y = torch.empty(M, 512, device=cuda)
+    cabi.call("omt_layernorm", x.to(cuda), 512, y, 512, g.to(cuda), b.to(cuda), M, 512, 1e-5, 0, 0, 0)
+    yp = torch.zeros(2, M, 512, dtype=torch.int16, device=cuda)
+    xp = torch.zeros(2, M, 512, dtype=torch.int16, device=cuda)
+    y2 = torch.empty(M, 512, device=cuda)
+    cabi.call("omt_layernorm_h", x.to(cuda), 512, y2, 512, yp[0], yp[1], xp[0], xp[1], 512, g.to(cuda), b.to(cuda), M, 512,
+              1e-5, 0, 0, 0)
+    assert torch.equal(y, y2)
+    tol = lambda t: 2.0 ** -19 * t.abs().max().item()
+    assert (_join(yp[0], yp[1], scheme) - y.cpu()).abs().max().item() <= tol(y.cpu())
+    assert (_join(xp[0], xp[1], scheme) - x).abs().max().item() <= tol(x)
+    cabi.call("omt_layernorm_h", x.to(cuda), 512, None, 0, yp[0], yp[1], None, None, 512, g.to(cuda), b.to(cuda), M, 512,
+              1e-5, 0, 0, 0)                                     # planes only
+    assert (_join(yp[0], yp[1], scheme) - y.cpu()).abs().max().item() <= tol(y.cpu())
+    # patch gather
+    shape = (2, 3, 5, 64, 64)
+    v = _rand(shape, 13, 0.5)
+    for is_first, K, rows in ((1, 192, 2 * 64), (0, 768, 2 * 64)):
+        lw, lb = _rand((K,), 14) + 1.0, _rand((K,), 15)
+        A = torch.empty(rows, K, device=cuda)
+        cabi.call("omt_patchify_ln", v.to(cuda), A, None, None, lw.to(cuda), lb.to(cuda), 2, 3, 5, 64, 64, 8, 4, is_first, 1e-5)
+        Ap = torch.zeros(2, rows, K, dtype=torch.int16, device=cuda)
+        cabi.call("omt_patchify_ln", v.to(cuda), None, Ap[0], Ap[1], lw.to(cuda), lb.to(cuda), 2, 3, 5, 64, 64, 8, 4, is_first,
+                  1e-5)
+        assert (_join(Ap[0], Ap[1], scheme) - A.cpu()).abs().max().item() <= tol(A.cpu())
+    # attention cores
+    nseq, N = 2, 256
+    Ma = nseq * N
+    qkv = torch.cat([_rand((Ma, 512), 30, 0.2), _rand((Ma, 512), 31, 0.2), _rand((Ma, 512), 32)], dim=1).contiguous().to(cuda)
+    p = qkv.data_ptr()
+    o = torch.empty(Ma, 512, device=cuda)
+    op = torch.zeros(2, Ma, 512, dtype=torch.int16, device=cuda)
+    for kern in (3, 1):
+        cabi.set_option("attn_kernel", kern)
+        cabi.call("omt_attn_spatial", p, 1536, p + 2048, 1536, p + 4096, 1536, o, None, None, 512, nseq, N, 8, 8.0)
+        cabi.call("omt_attn_spatial", p, 1536, p + 2048, 1536, p + 4096, 1536, None, op[0], op[1], 512, nseq, N, 8, 8.0)
+        assert (_join(op[0], op[1], scheme) - o.cpu()).abs().max().item() <= tol(o.cpu())
+    cabi.set_option("attn_kernel", 3)
+    bias = _rand((8, 64, 64), 33).to(cuda)
+    cabi.call("omt_attn_window", p, 1536, p + 2048, 1536, p + 4096, 1536, o, None, None, 512, bias, nseq, 16, 16, 8, 8, 0.125)
+    cabi.call("omt_attn_window", p, 1536, p + 2048, 1536, p + 4096, 1536, None, op[0], op[1], 512, bias, nseq, 16, 16, 8, 8,
+              0.125)
+    assert (_join(op[0], op[1], scheme) - o.cpu()).abs().max().item() <= tol(o.cpu())
+    cabi.call("omt_attn_temporal", p, 1536, p + 2048, 1536, p + 4096, 1536, o, None, None, 512, 2, 4, 64, 8, 8.0, 1)
+    cabi.call("omt_attn_temporal", p, 1536, p + 2048, 1536, p + 4096, 1536, None, op[0], op[1], 512, 2, 4, 64, 8, 8.0, 1)
+    assert (_join(op[0], op[1], scheme) - o.cpu()).abs().max().item() <= tol(o.cpu())

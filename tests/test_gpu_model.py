@@ -15,7 +15,7 @@ PIX_TOL = 1e-3
 
 
 def _math_modes():
-    return [m for m in os.environ.get("OMT_TEST_MATH", "fp32,3xtf32").split(",") if m]
+    return [m for m in os.environ.get("OMT_TEST_MATH", "fp32,3xtf32,f16x3").split(",") if m]
 
 
 @pytest.mark.parametrize("math", _math_modes())
@@ -38,11 +38,12 @@ def test_vq_encode_decode_matches_golden(cuda, name, math):
         assert torch.equal(rec2, rec)
 
 
+@pytest.mark.parametrize("math", _math_modes())
 @pytest.mark.parametrize("name", ["vae_vid5x64", "vae_img64"])
-def test_vae_matches_golden(cuda, name):
+def test_vae_matches_golden(cuda, name, math):
     fx = load_golden(name)
     cfg, sd, x = golden_setup(fx)
-    m = build_model(cfg, sd, cuda, "fp32")
+    m = build_model(cfg, sd, cuda, math)
     is_image = x.ndim == 4
     _orig = torch.randn
     try:       # the reference draws the noise from the global CPU RNG (vae.py:16); inject the recorded draw
@@ -100,6 +101,13 @@ def test_forward_log_image(cuda, math):
     assert (xr.cpu() - o[3]).abs().max().item() < PIX_TOL
     assert torch.equal(fr.cpu(), o[0]) and (frr.cpu() - o[1]).abs().max().item() < PIX_TOL
     assert m.codebook.call_cnt == 2
+    # encode() runs Codebook.forward too, so it moves the eval-time usage statistics (modules/codebook.py:133-138)
+    before = m.codebook.codebook_usage.clone()
+    idx = m.encode(xv.to(cuda), False)
+    assert m.codebook.call_cnt == 3
+    usage = torch.bincount(idx.reshape(-1).cpu(), minlength=8192).float() / idx.numel()
+    want = 0.99 * before.cpu() + 0.01 * usage
+    assert (m.codebook.codebook_usage.cpu() - want).abs().max().item() < 1e-7
 
 
 def test_shape_errors_match_reference(cuda):
@@ -113,11 +121,12 @@ def test_shape_errors_match_reference(cuda):
         build_model(cfg, W.make_state_dict(cfg, 0), torch.device("cpu")).encode(torch.zeros(1, 3, 64, 64), True)
 
 
-def test_determinism_and_batch_independence(cuda):
+@pytest.mark.parametrize("math", _math_modes())
+def test_determinism_and_batch_independence(cuda, math):
     """Samples are independent (the property batch-sharding relies on): a shard's codes equal the
     corresponding rows of the full batch."""
     cfg = oo.Config()
-    m = build_model(cfg, W.make_state_dict(cfg, 2), cuda, "fp32")
+    m = build_model(cfg, W.make_state_dict(cfg, 2), cuda, math)
     x = W.synthetic_input((3, 3, 5, 64, 64), 9).to(cuda)
     full = m.encode(x, False)
     again = m.encode(x, False)

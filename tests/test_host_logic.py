@@ -86,3 +86,25 @@ def test_unsupported_configurations_say_why():
     a = ob.canonical_args(["--attn_dropout", "0.1"])
     m = ob.OmniTokenizer_VQGAN(a)          # constructing is fine (training flag); the engine rejects it on first use
     assert m.args.attn_dropout == 0.1
+
+
+def _join(hi, lo, scheme):
+    if scheme == 1:
+        return hi.view(torch.float16).float() + lo.view(torch.bfloat16).float()
+    return hi.view(torch.float16).float() + lo.view(torch.float16).float() / 2048.0
+
+
+def test_f16x3_split_is_tight():
+    """Host-side operand split of the f16x3 path (layout.split_f16 == the device-side rule in csrc/omt_common.cuh):
+    |x - (hi + lo)| <= 2^-20 |x| with bf16 lo planes (scheme 1), 2^-22 |x| with scaled fp16 lo planes (scheme 2);
+    hi saturates instead of overflowing and lo carries the remainder."""
+    from omnitokenizer_b200 import layout as L
+    x = (torch.rand(4096, generator=torch.Generator().manual_seed(1)) - 0.5) * 60.0
+    for scheme, bound in ((1, 2.0 ** -20), (2, 2.0 ** -22)):
+        hi, lo = L.split_f16(x, scheme)
+        assert hi.dtype == torch.float16 and lo.dtype == (torch.bfloat16 if scheme == 1 else torch.float16)
+        assert ((_join(hi, lo, scheme) - x).abs() <= bound * x.abs() + 1e-30).all()
+    big = torch.tensor([1e6, -3e5, 65504.0, 7e-8])
+    hi, lo = L.split_f16(big, 1)
+    assert torch.isfinite(hi.float()).all() and torch.isfinite(lo.float()).all()
+    assert (_join(hi, lo, 1) - big).abs().max() < 4e3            # 8 significant bits left above the fp16 range
