@@ -50,7 +50,7 @@ int omt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* GEMM math selectors */
 #define OMT_MATH_FP32 0      /* CUDA-core FFMA, exact fp32 (parity anchor) */
 #define OMT_MATH_3XTF32 1    /* tcgen05 kind::tf32, error-compensated hi/lo split, fp32 accumulate in TMEM */
-#define OMT_MATH_F16X3 3     /* tcgen05 kind::f16 on pre-split fp16 hi / bf16 lo operand planes (omt_linear_h) */
+#define OMT_MATH_F16X3 3     /* tcgen05 kind::f16 on pre-split fp16 hi / lo operand planes (omt_linear_h) */
 
 /* C[M, N] = A[M, K] . W[N, K]^T (+ bias[N]) (+ residual[M, N]); nn.Linear everywhere on the path:
  * attention.py:411 (to_q / to_kv), :486 (to_out), :271/:288 (window qkv / proj), :164/:167 (FF),
@@ -90,7 +90,7 @@ int omt_layernorm(const float* x, int ldx, float* y, int ldy, const float* w, co
  * video (B, Cin, T, H, W) fp32 contiguous.  first=1: frame 0, rows (b,h,w), features (c,p1,p2);
  * first=0: frames 1.., rows (b,t,h,w), features (c,pt,p1,p2).  A is [rows, K] dense.
  * ln_w == ln_b == NULL: plain patch gather (im2col of the strided Conv3d of patch_embed='cnn', omnitokenizer.py:823-838).
- * A_hi != NULL: the rows are written as fp16 hi / bf16 lo operand planes [rows, K] instead of A (A may be NULL). */
+ * A_hi != NULL: the rows are written as fp16 hi / lo operand planes [rows, K] instead of A (A may be NULL). */
 int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uint16_t* A_lo, const float* ln_w, const float* ln_b,
                     int B, int Cin, int T, int H, int W, int p, int pt, int first, float eps,
                     omt_stream_t stream);
@@ -98,6 +98,13 @@ int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uint16_t* A_lo
 /* Inverse Rearrange of to_pixels (omnitokenizer.py:1008 / :1015): P [rows, K] -> video (B,Cin,T,H,W). */
 int omt_unpatchify(const float* P, float* video, int B, int Cin, int T, int H, int W, int p, int pt,
                    int first, omt_stream_t stream);
+
+/* Un-patchify fused with the consumers' uint8 conversion: u8 = trunc(clamp(x * mul + add, lo, hi) * post), written
+ * channels-LAST (B, T, H, W, Cin).  (mul, add, lo, hi, post) = (1, .5, 0, 1, 255) is vqgan_eval.py:139,147-148
+ * `(clamp(x_recons + 0.5, 0, 1) * 255).byte()` and Latte's sample_ddp.py:206; (255, 128, 0, 255, 1) is DiT's
+ * sample_ddp.py:163.  Each step rounds in fp32 like the torch expression, so the bytes are identical to it. */
+int omt_unpatchify_u8(const float* P, uint8_t* out, int B, int Cin, int T, int H, int W, int p, int pt,
+                      int first, float mul, float add, float lo, float hi, float post, omt_stream_t stream);
 
 /* PEG (attention.py:298-338) + residual: y[r,:] = x[r,:] + bias + sum_k w[k,:] * x[nbr[r % rows_per_b, k] , :]
  * nbr: int32 [rows_per_b, 27] canonical neighbour rows inside one batch element, -1 = zero padding
@@ -122,7 +129,7 @@ int omt_qk_prep(float* q, int ldq, float* k, int ldk, const float* q_scale, cons
 
 /* Full (non-causal) attention over n_seq sequences of N contiguous canonical rows, head dim 64:
  * o = softmax(scale * q k^T) v   (attention.py:451, SDPA branch: no additive bias).  N % 64 == 0.
- * All three attention cores: when o_hi != NULL the result is written as fp16 hi / bf16 lo operand planes
+ * All three attention cores: when o_hi != NULL the result is written as fp16 hi / lo operand planes
  * (leading dimension ldo) for the out-projection GEMM instead of fp32 o (o may then be NULL). */
 int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
                      float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, int n_seq, int N, int heads, float scale,
@@ -162,9 +169,9 @@ int omt_post_vq(const int64_t* idx, const float* E, const float* zc, const float
                 omt_stream_t stream);
 
 /* ---- f16x3 path: operands as 16-bit planes ------------------------------------------------------------
- * An fp32 matrix X is carried as hi = fp16(X) (round to nearest, saturating) and lo = bf16(X - hi), two
- * uint16 matrices with a common leading dimension.  Producers below write the planes directly; weights are
- * split once on the host.  ("f16_scheme" = 2 switches the lo planes to fp16((X - hi) * 2^11), see omt_set_option.) */
+ * An fp32 matrix X is carried as hi = fp16(X) (round to nearest, saturating) and lo = fp16((X - hi) * 2^11), two
+ * uint16 matrices with a common leading dimension: X ~= hi + lo * 2^-11 to 2^-23 |X| for |X| < 65504.
+ * Producers below write the planes directly; weights are split once on the host. */
 typedef struct omt_linear_h_args {
   const uint16_t* a_hi; const uint16_t* a_lo;      /* A planes [M, lda] */
   const uint16_t* a2_hi; const uint16_t* a2_lo;    /* optional second A (dual-A form, columns >= n_split), same lda / row map */
@@ -194,8 +201,8 @@ int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, 
 /* Tuning knobs (process-wide): "pdl" = 0 (default; measured 2-4 % slower when on) | 1 programmatic dependent launch;
  * "peg_kernel" = 3 (default) | 4 (cp.async gather + packed f32x2 FMAs; bit-identical);
  * "attn_kernel" = 3 (default: tcgen05 spatial attention core when N % 128 == 0) | 1 (CUDA-core fp32);
- * "f16_scheme" = 1 (default: bf16 lo planes, one TMEM accumulator) | 2 (fp16 lo planes scaled by 2^11, cross terms in a
- * second accumulator) -- every producer and omt_linear_h follow the process-wide value. */
+ * "f16_bn" = 256 (default: 256 x 256 tiles, one TMEM buffer released as soon as the epilogue has drained it into
+ * registers) | 128 (256 x 128 tiles, double-buffered accumulators) for omt_linear_h. */
 int omt_set_option(const char* name, int value);
 
 #ifdef __cplusplus

@@ -50,6 +50,7 @@ SIGNATURES = {
                                 c_void_p, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
     "omt_patchify_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_float, c_void_p]),
     "omt_unpatchify": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "omt_unpatchify_u8": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_float] * 5 + [c_void_p]),
     "omt_peg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "omt_peg_volume": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "omt_qk_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -134,7 +135,7 @@ def linear_h(**kw):
 
 
 # process-wide kernel selectors and their library defaults (omt_set_option); tests restore these after flipping them
-DEFAULT_OPTIONS = {"attn_kernel": 3, "peg_kernel": 3, "f16_scheme": 1}
+DEFAULT_OPTIONS = {"attn_kernel": 3, "peg_kernel": 3, "f16_bn": 256}
 
 
 def set_option(name: str, value: int):

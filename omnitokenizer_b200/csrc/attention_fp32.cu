@@ -21,7 +21,7 @@ struct AttnArgs {
   const float* k; int ldk;
   const float* v; int ldv;
   float* o; int ldo;
-  uint16_t* o_hi; uint16_t* o_lo; int scheme;   // optional fp16 hi / bf16 lo operand planes instead of o (ld = ldo)
+  uint16_t* o_hi; uint16_t* o_lo;   // optional fp16 hi / bf16 lo operand planes instead of o (ld = ldo)
   const float* bias;   // window: [heads][64][64]
   int N;               // tokens per frame
   int h, w, ws;        // window mode
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256, 2) attn_flash_kernel(const AttnArgs a) {
     const long long row = token_row<WINDOW>(a, seq, qt * AQ + ty * 4 + i);
     const float inv = 1.0f / lrow[i];
     const float4 ov = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
-    if (a.o_hi != nullptr) store_split4(a.o_hi, a.o_lo, (size_t)(row * a.ldo + head * AD + tx * 4), ov, a.scheme);
+    if (a.o_hi != nullptr) store_split4(a.o_hi, a.o_lo, (size_t)(row * a.ldo + head * AD + tx * 4), ov);
     else *reinterpret_cast<float4*>(a.o + row * a.ldo + head * AD + tx * 4) = ov;
   }
 }
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) attn_temporal_kernel(const float* __restr
                                                             const float* __restrict__ k, int ldk,
                                                             const float* __restrict__ v, int ldv,
                                                             float* __restrict__ o, uint16_t* __restrict__ o_hi,
-                                                            uint16_t* __restrict__ o_lo, int scheme, int ldo, int B,
+                                                            uint16_t* __restrict__ o_lo, int ldo, int B,
                                                             int N, int heads, float scale, int causal) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) attn_temporal_kernel(const float* __restr
       }
     }
     const float2 ov = make_float2(ox / den, oy / den);
-    if (o_hi != nullptr) store_split2(o_hi, o_lo, row * ldo + col, ov, scheme);
+    if (o_hi != nullptr) store_split2(o_hi, o_lo, row * ldo + col, ov);
     else *reinterpret_cast<float2*>(o + row * ldo + col) = ov;
   }
 }
@@ -241,7 +241,7 @@ static int launch_temporal(const float* q, int ldq, const float* k, int ldk, con
                            cudaStream_t st) {
   const long long warps = (long long)B * N * heads;
   const unsigned blocks = (unsigned)((warps + 7) / 8);
-  OMT_CUDA(launch_k(attn_temporal_kernel<T>, dim3(blocks), dim3(256), 0, st, q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, g_f16_scheme, ldo, B, N, heads, scale, causal));
+  OMT_CUDA(launch_k(attn_temporal_kernel<T>, dim3(blocks), dim3(256), 0, st, q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, ldo, B, N, heads, scale, causal));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -288,7 +288,7 @@ extern "C" int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk
     return launch_attn_tc3(q, ldq, k, ldk, v, ldv, o, o_hi, o_lo, ldo, n_seq, N, heads, scale, (cudaStream_t)stream);
   rc = set_flash_smem();
   if (rc) return rc;
-  AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, o_hi, o_lo, g_f16_scheme, nullptr, N, 0, 0, 0, scale};
+  AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, o_hi, o_lo, nullptr, N, 0, 0, 0, scale};
   dim3 grid(N / AQ, heads, n_seq);
   OMT_CUDA(launch_k(attn_flash_kernel<false>, grid, dim3(256), 65536, (cudaStream_t)stream, a));
   OMT_LAUNCH_CHECK();
@@ -309,7 +309,7 @@ extern "C" int omt_attn_window(const float* q, int ldq, const float* k, int ldk,
   if (n_seq == 0) return OMT_OK;
   rc = set_flash_smem();
   if (rc) return rc;
-  AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, o_hi, o_lo, g_f16_scheme, bias, h * w, h, w, ws, scale};
+  AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, o_hi, o_lo, bias, h * w, h, w, ws, scale};
   dim3 grid((unsigned)n_seq, heads, 1);
   OMT_CUDA(launch_k(attn_flash_kernel<true>, grid, dim3(256), 65536, (cudaStream_t)stream, a));
   OMT_LAUNCH_CHECK();

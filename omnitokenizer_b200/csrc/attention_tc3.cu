@@ -39,7 +39,7 @@ constexpr uint32_t IDESC_KK = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(6
 
 struct Args {
   float* o; int ldo;
-  uint16_t* o_hi; uint16_t* o_lo; int scheme;   // optional operand planes instead of o
+  uint16_t* o_hi; uint16_t* o_lo;   // optional operand planes instead of o
   int N;
   float scale_log2;
 };
@@ -316,7 +316,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 ov = make_float4(o_acc[i] * inv, o_acc[i + 1] * inv, o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-      if (a.o_hi != nullptr) store_split4(a.o_hi, a.o_lo, ooff + i, ov, a.scheme);
+      if (a.o_hi != nullptr) store_split4(a.o_hi, a.o_lo, ooff + i, ov);
       else *reinterpret_cast<float4*>(a.o + ooff + i) = ov;
     }
   }
@@ -373,7 +373,7 @@ int launch_attn_tc3(const float* q, int ldq, const float* k, int ldk, const floa
     OMT_CUDA(cudaFuncSetAttribute(attn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr[dev] = true;
   }
-  Args a{o, ldo, o_hi, o_lo, g_f16_scheme, N, scale * 1.4426950408889634f};
+  Args a{o, ldo, o_hi, o_lo, N, scale * 1.4426950408889634f};
   dim3 grid(N / QT, heads, n_seq);
   OMT_CUDA(launch_k(attn_tc3_kernel, grid, dim3(THREADS), SMEM, st, tmQ, tmK, tmV, a));
   OMT_LAUNCH_CHECK();

@@ -2,12 +2,12 @@
 //
 //   C[M,N] = A[M,K] . W[N,K]^T (+bias)(+residual) | GEGLU | rope+l2norm+scale,   fp32-grade accuracy.
 //
-// Every fp32 operand x is carried as TWO 16-bit planes, hi = fp16(x) and lo = bf16(x - hi) (omt_common.cuh: 11 + 8
-// significant bits, error 2^-21 |x| like the tf32 hi/lo split), written ONCE by whatever kernel produced x (LayerNorm,
-// the attention cores, the GEGLU epilogue of this kernel; weights at pack time).  The product is
-//       A.W ~= A_lo.W_hi + A_hi.W_lo + A_hi.W_hi
-// three kind::f16 MMAs into ONE fp32 TMEM accumulator (bf16 has fp32's exponent range, so lo needs no scaling; the
-// a/b formats are selected per operand in the instruction descriptor).  Against the 3xTF32 kernel (gemm_tc2.cu):
+// Every fp32 operand x is carried as TWO fp16 planes, hi = fp16(x) and lo = fp16((x - hi) * 2^11) (omt_common.cuh:
+// 11 + 11 significant bits, error <= 2^-23 |x|), written ONCE by whatever kernel produced x (LayerNorm, the attention
+// cores, the GEGLU epilogue of this kernel; weights at pack time).  The product is
+//       A.W ~= A_hi.W_hi + 2^-11 (A_hi.W_lo + A_lo.W_hi)
+// three kind::f16 MMAs per k-step: the first into the MAIN fp32 TMEM accumulator, the two cross products into a second
+// one that the epilogue folds in with an exact power-of-two scale.  Against the 3xTF32 kernel (gemm_tc2.cu):
 //   * 16-bit MMAs run at twice the tf32 rate -> the exactness tax drops from 3 to 1.5 tf32-equivalents per product;
 //   * the operands arrive in their final shared-memory form by TMA: no transform warps, no generic-proxy round trip
 //     between the TMA landing and the MMA (the k-block critical path is TMA -> mbarrier -> tcgen05.mma);
@@ -18,12 +18,13 @@
 //              credited to the LEADER's full[s] (cp.async.bulk.tensor .cta_group::2)
 //   warp 1     TMEM alloc; in the leader: tcgen05.mma issue (elect.sync), multicast tcgen05.commit -> empty[s] /
 //              tmem_full[acc] of both CTAs
-//   warps 2-9  epilogue, lane = accumulator row (the tcgen05.ld layout is never transposed through registers):
-//              fp32 outputs are staged as SWIZZLE_128B 32 x 32 boxes in a warp-private slab and leave by TMA STORE;
-//              GEGLU writes the fp16 / bf16 planes of U directly (32-byte segments per row);
-//              accumulators are double-buffered in TMEM (2 x BN columns), so this overlaps the next tile's main loop.
-// Template NACC = 2 is the fallback operand format (lo = fp16((x - hi) * 2^11), cross terms in a second accumulator
-// scaled by 2^-11 in the epilogue) should a box refuse mixed fp16 x bf16 descriptors; BN = 128 then.
+//   warps 2-9  epilogue, lane = accumulator row (the tcgen05.ld layout is never transposed through registers): each warp
+//              DRAINS its 32 x BN/2 slice of both accumulators into registers, releases the TMEM buffer at once, and only
+//              then does the bias / residual / GELU / rope work and the stores -- fp32 outputs are staged as SWIZZLE_128B
+//              32 x 32 boxes in a warp-private slab and leave by TMA STORE; GEGLU writes the planes of U directly.
+// TMEM budget (512 columns, two accumulators per tile): BN = 256 -> one buffer (the early release keeps the tensor pipe
+// idle only for the drain); BN = 128 -> two buffers (epilogue fully overlapped, but twice the A traffic from L2 and
+// N = 128 MMAs).  omt_set_option("f16_bn", 128 | 256) selects; profiles/ has the A/B.
 #include "omt_common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
@@ -43,6 +44,7 @@ template <int BN> struct Cfg {
   static constexpr int W_BYTES = (BN / 2) * BK * 2;                 // per plane, per CTA
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;     // A_hi, A_lo, W_hi, W_lo
   static constexpr int STAGES = (BN == 256) ? 3 : 4;                // 192 KiB either way
+  static constexpr int NBUF = 512 / (2 * BN);                       // TMEM accumulator buffers (main + cross per buffer)
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * SLAB_BYTES + 1024;
 };
 
@@ -77,19 +79,16 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, int NACC, int EPI>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
                 const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                 const __grid_constant__ CUtensorMap tmC, const HArgs g) {
   using C_ = Cfg<BN>;
-  constexpr int W_BYTES = C_::W_BYTES, STAGE_BYTES = C_::STAGE_BYTES, STAGES = C_::STAGES;
-  static_assert(2 * NACC * BN <= 512, "TMEM: NACC accumulators of BN columns, double-buffered");
-  // operand formats: NACC == 1 -> lo planes are bf16; NACC == 2 -> every plane is fp16
-  constexpr uint32_t ID_HH = idesc_f16(256, BN, false, false);
-  constexpr uint32_t ID_LH = idesc_f16(256, BN, NACC == 1, false);      // A = lo plane, B = hi plane
-  constexpr uint32_t ID_HL = idesc_f16(256, BN, false, NACC == 1);      // A = hi plane, B = lo plane
+  constexpr int W_BYTES = C_::W_BYTES, STAGE_BYTES = C_::STAGE_BYTES, STAGES = C_::STAGES, NBUF = C_::NBUF;
+  static_assert(NBUF == 1 || NBUF == 2, "TMEM: main + cross accumulators of BN columns, NBUF buffers");
+  constexpr uint32_t IDESC = idesc_f16(256, BN, false, false);          // fp16 x fp16 -> fp32, UMMA 256 x BN x 16
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (SW128 tiles) by POINTER OFFSET so the pointer keeps the shared address space
@@ -175,11 +174,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     if (leader) {
       uint32_t it = 0, tcount = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
-        const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+        const uint32_t acc = tcount % NBUF, acc_ph = (tcount / NBUF) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
-        const uint32_t d_main = tmem_base + acc * (NACC * BN);
-        const uint32_t d_cross = d_main + (NACC - 1) * BN;              // == d_main for the single-accumulator form
+        const uint32_t d_main = tmem_base + acc * (2 * BN);
+        const uint32_t d_cross = d_main + BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -192,15 +191,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t adv = (uint64_t)(k * 32 >> 4);             // 16 elements = 32 bytes inside the swizzle row
-              if (NACC == 1) {
-                mma_f16_pair(d_main, d_alo + adv, d_whi + adv, ID_LH, (kb | k) != 0);
-                mma_f16_pair(d_main, d_ahi + adv, d_wlo + adv, ID_HL, 1);
-                mma_f16_pair(d_main, d_ahi + adv, d_whi + adv, ID_HH, 1);
-              } else {
-                mma_f16_pair(d_cross, d_alo + adv, d_whi + adv, ID_LH, (kb | k) != 0);
-                mma_f16_pair(d_cross, d_ahi + adv, d_wlo + adv, ID_HL, 1);
-                mma_f16_pair(d_main, d_ahi + adv, d_whi + adv, ID_HH, (kb | k) != 0);
-              }
+              mma_f16_pair(d_cross, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
+              mma_f16_pair(d_cross, d_ahi + adv, d_wlo + adv, IDESC, 1);
+              mma_f16_pair(d_main, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
             }
             tc_commit_pair(&empty[s]);
             if (kb == num_kb - 1) tc_commit_pair(&tmem_full[acc]);
@@ -219,7 +212,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t tcount = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
-      const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+      const uint32_t acc = tcount % NBUF, acc_ph = (tcount / NBUF) & 1;
       int m_blk, n_blk;
       decode_tile(tile, g.num_m_blk, g.num_n_blk, num_clusters, m_blk, n_blk);
       const int mw = m_blk * (2 * BM) + (int)rank * BM + q * 32;     // first row of this warp
@@ -230,24 +223,44 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       // TMA store coordinates of the warp's 32 rows (a row-map segment is a multiple of 32 rows)
       int cm1 = mw, cm2 = 0;
       if (g.c_seg > 0) { cm1 = mw % g.c_seg; cm2 = mw / g.c_seg; }
-      const uint32_t t_main = tmem_base + lane_addr + acc * (NACC * BN) + (uint32_t)(hf * (BN / 2));
+      const uint32_t t_main = tmem_base + lane_addr + acc * (2 * BN) + (uint32_t)(hf * (BN / 2));
 
-      // accumulator chunk c (32 columns) of this lane's row, cross terms folded in for the two-accumulator form
-      auto load_acc = [&](int c, float (&v)[32]) {
-        tmem_ld32(t_main + (uint32_t)(c * 32), v);
-        if (NACC == 2) {
-          float x[32];
-          tmem_ld32(t_main + (uint32_t)(BN + c * 32), x);
+      // residual row segments (8 x 16 bytes per lane and chunk) ride in ONE register buffer: the next chunk's loads are
+      // issued right after the current chunk's adds, so their latency hides behind the box store
+      const float* rrow = (EPI == OMT_EPI_NONE && g.residual != nullptr) ? g.residual + (size_t)prow * g.ldr : nullptr;
+      float4 res[8];
+      auto load_res = [&](int c) {
+        const int n = n0 + c * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(x[j], 1.0f / 2048.0f, v[j]);
+        for (int i = 0; i < 8; ++i) {
+          res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rrow != nullptr && row_ok && n < g.N) res[i] = *reinterpret_cast<const float4*>(rrow + n + 4 * i);
         }
       };
+      if (EPI == OMT_EPI_NONE && NBUF == 2) load_res(0);      // two buffers = 64 accumulator registers: room to prefetch
+
+      // ---- drain: this lane's row of both accumulators -> registers (main + cross * 2^-11), then release the buffer
+      float v[CH][32];
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float x[32];
+        tmem_ld32(t_main + (uint32_t)(BN + c * 32), x);
+        tmem_ld32(t_main + (uint32_t)(c * 32), v[c]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c][j] = fmaf(x[j], 1.0f / F16X3_LO_SCALE, v[c][j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa(smem_u32(&tmem_empty[acc]), 0));
+
       // stage a finished 32 x 32 fp32 box in the slab (swizzled, conflict-free 16-byte stores) and hand it to the TMA
-      auto store_box = [&](int n, const float (&v)[32]) {
+      auto store_box = [&](int n, const float (&t)[32]) {
         if (lane == 0) bulk_wait_read<0>();           // the previous box has left the slab
         __syncwarp();
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) sts128(slab + sw128(lane, c4), v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        for (int c4 = 0; c4 < 8; ++c4) sts128(slab + sw128(lane, c4), t[4 * c4], t[4 * c4 + 1], t[4 * c4 + 2], t[4 * c4 + 3]);
         fence_async_smem();
         __syncwarp();
         if (lane == 0 && mw < g.M) {
@@ -259,144 +272,115 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       if constexpr (EPI == OMT_EPI_QKV) {
         // ---- q / k heads: rope + l2norm + per-dim scale (attention.py:417-421, 435-437); a head = two chunks, all
         //      64 values of a row live in one lane, so the norm is thread-local
-        mbar_wait(&tmem_full[acc], acc_ph);
-        tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int hd = 0; hd < CH / 2; ++hd) {
           const int nh = n0 + hd * 64;
-          if (nh >= g.N) break;
-          float va[32], vb[32];
-          load_acc(hd * 2, va);
-          load_acc(hd * 2 + 1, vb);
-          if (nh < g.qk_cols) {
-            if (g.rope_cos != nullptr) {
-              const int pos = (row_ok ? m : 0) % g.tokens;
-              const float4* ct = reinterpret_cast<const float4*>(g.rope_cos + (size_t)pos * 32);
-              const float4* st = reinterpret_cast<const float4*>(g.rope_sin + (size_t)pos * 32);
+          if (nh < g.N) {
+            float (&va)[32] = v[2 * hd];
+            float (&vb)[32] = v[2 * hd + 1];
+            if (nh < g.qk_cols) {
+              if (g.rope_cos != nullptr) {
+                const int pos = (row_ok ? m : 0) % g.tokens;
+                const float4* ct = reinterpret_cast<const float4*>(g.rope_cos + (size_t)pos * 32);
+                const float4* st = reinterpret_cast<const float4*>(g.rope_sin + (size_t)pos * 32);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {          // 4 complex pairs per float4 of the table
-                const float4 c = __ldg(ct + i), s = __ldg(st + i);
-                const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+                for (int i = 0; i < 4; ++i) {          // 4 complex pairs per float4 of the table
+                  const float4 c = __ldg(ct + i), s = __ldg(st + i);
+                  const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                  const float x = va[8 * i + 2 * p], y = va[8 * i + 2 * p + 1];
-                  va[8 * i + 2 * p] = x * cc[p] - y * ss[p];
-                  va[8 * i + 2 * p + 1] = x * ss[p] + y * cc[p];
+                  for (int p = 0; p < 4; ++p) {
+                    const float x = va[8 * i + 2 * p], y = va[8 * i + 2 * p + 1];
+                    va[8 * i + 2 * p] = x * cc[p] - y * ss[p];
+                    va[8 * i + 2 * p + 1] = x * ss[p] + y * cc[p];
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 c = __ldg(ct + 4 + i), s = __ldg(st + 4 + i);
+                  const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                  for (int p = 0; p < 4; ++p) {
+                    const float x = vb[8 * i + 2 * p], y = vb[8 * i + 2 * p + 1];
+                    vb[8 * i + 2 * p] = x * cc[p] - y * ss[p];
+                    vb[8 * i + 2 * p + 1] = x * ss[p] + y * cc[p];
+                  }
                 }
               }
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 c = __ldg(ct + 4 + i), s = __ldg(st + 4 + i);
-                const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+              for (int j = 0; j < 32; j += 4) {
+                s0 = fmaf(va[j], va[j], s0); s1 = fmaf(va[j + 1], va[j + 1], s1);
+                s2 = fmaf(va[j + 2], va[j + 2], s2); s3 = fmaf(va[j + 3], va[j + 3], s3);
+              }
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                  const float x = vb[8 * i + 2 * p], y = vb[8 * i + 2 * p + 1];
-                  vb[8 * i + 2 * p] = x * cc[p] - y * ss[p];
-                  vb[8 * i + 2 * p + 1] = x * ss[p] + y * cc[p];
-                }
+              for (int j = 0; j < 32; j += 4) {
+                s0 = fmaf(vb[j], vb[j], s0); s1 = fmaf(vb[j + 1], vb[j + 1], s1);
+                s2 = fmaf(vb[j + 2], vb[j + 2], s2); s3 = fmaf(vb[j + 3], vb[j + 3], s3);
+              }
+              const float inv = 1.0f / fmaxf(sqrtf((s0 + s1) + (s2 + s3)), 1e-12f);
+              const float4* scv = reinterpret_cast<const float4*>((nh < g.qk_cols / 2) ? g.q_scale : g.k_scale);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 sa = __ldg(scv + i), sb = __ldg(scv + 8 + i);
+                va[4 * i] = va[4 * i] * inv * sa.x; va[4 * i + 1] = va[4 * i + 1] * inv * sa.y;
+                va[4 * i + 2] = va[4 * i + 2] * inv * sa.z; va[4 * i + 3] = va[4 * i + 3] * inv * sa.w;
+                vb[4 * i] = vb[4 * i] * inv * sb.x; vb[4 * i + 1] = vb[4 * i + 1] * inv * sb.y;
+                vb[4 * i + 2] = vb[4 * i + 2] * inv * sb.z; vb[4 * i + 3] = vb[4 * i + 3] * inv * sb.w;
               }
             }
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              s0 = fmaf(va[j], va[j], s0); s1 = fmaf(va[j + 1], va[j + 1], s1);
-              s2 = fmaf(va[j + 2], va[j + 2], s2); s3 = fmaf(va[j + 3], va[j + 3], s3);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              s0 = fmaf(vb[j], vb[j], s0); s1 = fmaf(vb[j + 1], vb[j + 1], s1);
-              s2 = fmaf(vb[j + 2], vb[j + 2], s2); s3 = fmaf(vb[j + 3], vb[j + 3], s3);
-            }
-            const float inv = 1.0f / fmaxf(sqrtf((s0 + s1) + (s2 + s3)), 1e-12f);
-            const float4* scv = reinterpret_cast<const float4*>((nh < g.qk_cols / 2) ? g.q_scale : g.k_scale);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 sa = __ldg(scv + i), sb = __ldg(scv + 8 + i);
-              va[4 * i] = va[4 * i] * inv * sa.x; va[4 * i + 1] = va[4 * i + 1] * inv * sa.y;
-              va[4 * i + 2] = va[4 * i + 2] * inv * sa.z; va[4 * i + 3] = va[4 * i + 3] * inv * sa.w;
-              vb[4 * i] = vb[4 * i] * inv * sb.x; vb[4 * i + 1] = vb[4 * i + 1] * inv * sb.y;
-              vb[4 * i + 2] = vb[4 * i + 2] * inv * sb.z; vb[4 * i + 3] = vb[4 * i + 3] * inv * sb.w;
-            }
+            store_box(nh, va);
+            if (nh + 32 < g.N) store_box(nh + 32, vb);
           }
-          store_box(nh, va);
-          if (nh + 32 < g.N) store_box(nh + 32, vb);
         }
       } else if constexpr (EPI == OMT_EPI_GEGLU) {
-        // ---- packed columns (2j, 2j+1) = (value_j, gate_j): U[:, j] = gelu_erf(gate) * value, written as the fp16 hi /
-        //      bf16 lo planes the second FeedForward GEMM reads (16 outputs = one 32-byte segment per row and plane)
-        mbar_wait(&tmem_full[acc], acc_ph);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < CH; ++c) {
-          const int n = n0 + c * 32;
-          if (n >= g.N) break;
-          float v[32];
-          load_acc(c, v);
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float o0 = gelu_erf(v[4 * i + 1]) * v[4 * i];
-            const float o1 = gelu_erf(v[4 * i + 3]) * v[4 * i + 2];
-            if (NACC == 1) {
-              split2(o0, o1, hi[i], lo[i]);
-            } else {
-              hi[i] = pack_f16x2_sat(o0, o1);
-              const float2 h = unpack_f16x2(hi[i]);
-              lo[i] = pack_f16x2_sat((o0 - h.x) * 2048.0f, (o1 - h.y) * 2048.0f);
-            }
-          }
-          if (row_ok) {
-            const size_t off = (size_t)prow * g.ldu + (n >> 1);
-            uint4* ph = reinterpret_cast<uint4*>(g.u_hi + off);
-            uint4* pl = reinterpret_cast<uint4*>(g.u_lo + off);
-            ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          }
-        }
-      } else {
-        // ---- plain: (+bias)(+residual), fp32 box by TMA store.  The residual row segment of the NEXT chunk is fetched
-        //      (8 x 16 bytes per lane) before this chunk is processed, so its latency hides behind the TMEM read + store
-        float4 res[2][8];
-        const float* rrow = g.residual != nullptr ? g.residual + (size_t)prow * g.ldr : nullptr;
-        auto load_res = [&](int c, float4 (&dst)[8]) {
-          const int n = n0 + c * 32;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rrow != nullptr && row_ok && n < g.N) dst[i] = *reinterpret_cast<const float4*>(rrow + n + 4 * i);
-          }
-        };
-        load_res(0, res[0]);
-        mbar_wait(&tmem_full[acc], acc_ph);
-        tc_fence_after();
+        // ---- packed columns (2j, 2j+1) = (value_j, gate_j): U[:, j] = gelu_erf(gate) * value, written as the fp16 hi / lo
+        //      planes the second FeedForward GEMM reads (16 outputs = one 32-byte segment per row and plane)
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const int n = n0 + c * 32;
           if (n < g.N) {
-            if (c + 1 < CH) load_res(c + 1, res[(c + 1) & 1]);
-            float v[32];
-            load_acc(c, v);
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float o0 = gelu_erf(v[c][4 * i + 1]) * v[c][4 * i];
+              const float o1 = gelu_erf(v[c][4 * i + 3]) * v[c][4 * i + 2];
+              split2(o0, o1, hi[i], lo[i]);
+            }
+            if (row_ok) {
+              const size_t off = (size_t)prow * g.ldu + (n >> 1);
+              uint4* ph = reinterpret_cast<uint4*>(g.u_hi + off);
+              uint4* pl = reinterpret_cast<uint4*>(g.u_lo + off);
+              ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+          }
+        }
+      } else {
+        // ---- plain: (+bias)(+residual), fp32 box by TMA store
+        if (NBUF == 1) load_res(0);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int n = n0 + c * 32;
+          if (n < g.N) {
             if (g.bias != nullptr) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n) + i);
-                v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                v[c][4 * i] += bb.x; v[c][4 * i + 1] += bb.y; v[c][4 * i + 2] += bb.z; v[c][4 * i + 3] += bb.w;
               }
             }
             if (g.residual != nullptr) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 r = res[c & 1][i];
-                v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+                const float4 r = res[i];
+                v[c][4 * i] += r.x; v[c][4 * i + 1] += r.y; v[c][4 * i + 2] += r.z; v[c][4 * i + 3] += r.w;
               }
+              if (c + 1 < CH) load_res(c + 1);
             }
-            store_box(n, v);
+            store_box(n, v[c]);
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(mapa(smem_u32(&tmem_empty[acc]), 0));
     }
     if (lane == 0) bulk_wait<0>();      // every box has been written out before the CTA (and its shared memory) retires
     __syncwarp();
@@ -446,9 +430,9 @@ static int row_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void
   return encode_map(m, dt, base, 3, dims, strides, box);
 }
 
-template <int BN, int NACC, int EPI>
+template <int BN, int EPI>
 static int launch(const CUtensorMap* maps, const HArgs& g, cudaStream_t st) {
-  auto kern = gemm_f16_kernel<BN, NACC, EPI>;
+  auto kern = gemm_f16_kernel<BN, EPI>;
   static bool attr[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -476,13 +460,12 @@ static int launch(const CUtensorMap* maps, const HArgs& g, cudaStream_t st) {
 
 }  // namespace f16g
 
-int g_f16_scheme = 1;   // omt_set_option("f16_scheme", 1|2): 1 = bf16 lo planes, one accumulator; 2 = scaled fp16 lo planes, two accumulators
+int g_f16_bn = 256;   // omt_set_option("f16_bn", 128|256): tile N (256: one TMEM buffer, early release; 128: two buffers)
 
-// A planes: [M, lda] 16-bit; W planes: [n_pad, K] 16-bit (rows padded to 256); C fp32 (plain / QKV) or U planes (GEGLU)
+// A planes: [M, lda] fp16; W planes: [n_pad, K] fp16 (rows padded to 256); C fp32 (plain / QKV) or U planes (GEGLU)
 int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   using namespace f16g;
-  const int scheme = g_f16_scheme;
-  const int BN = scheme == 1 ? 256 : 128;
+  const int BN = g_f16_bn;
   OMT_REQUIRE(a.K % BK == 0 && a.lda % 8 == 0, "omt_linear_h: K=%d must be a multiple of 64 and lda %% 8 == 0", a.K);
   if (a.a_seg > 0)
     OMT_REQUIRE(a.a_seg % 64 == 0 && a.M % a.a_seg == 0, "omt_linear_h: A row-map segment %d must be a multiple of 64 dividing M=%d", a.a_seg, a.M);
@@ -491,8 +474,7 @@ int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   OMT_REQUIRE(a.N % 32 == 0, "omt_linear_h: N=%d must be a multiple of 32", a.N);
   if (a.a2_hi != nullptr) OMT_REQUIRE(a.n_split > 0 && a.n_split % 256 == 0, "omt_linear_h: n_split=%d must be a multiple of 256", a.n_split);
   const int n_pad = (a.N + 255) / 256 * 256;
-  const CUtensorMapDataType dt_hi = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  const CUtensorMapDataType dt_lo = scheme == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType dt_hi = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, dt_lo = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap maps[7];
   int rc;
   if ((rc = row_map(&maps[0], dt_hi, 2, a.a_hi, a.lda, a.M, a.K, a.a_seg, a.a_seg_stride, a.a_seg_off, BK, 64))) return rc;
@@ -523,8 +505,7 @@ int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   g.u_hi = a.u_hi; g.u_lo = a.u_lo; g.ldu = a.ldu;
   g.rope_cos = a.rope_cos; g.rope_sin = a.rope_sin; g.q_scale = a.q_scale; g.k_scale = a.k_scale;
   g.qk_cols = a.qk_cols; g.tokens = a.tokens > 0 ? a.tokens : 1;
-#define OMT_F16_LAUNCH(EPI_)                                                      \
-  (scheme == 1 ? launch<256, 1, EPI_>(maps, g, st) : launch<128, 2, EPI_>(maps, g, st))
+#define OMT_F16_LAUNCH(EPI_) (BN == 256 ? launch<256, EPI_>(maps, g, st) : launch<128, EPI_>(maps, g, st))
   if (a.epilogue == OMT_EPI_QKV) return OMT_F16_LAUNCH(OMT_EPI_QKV);
   if (a.epilogue == OMT_EPI_GEGLU) return OMT_F16_LAUNCH(OMT_EPI_GEGLU);
   return OMT_F16_LAUNCH(OMT_EPI_NONE);

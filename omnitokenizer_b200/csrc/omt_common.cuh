@@ -47,8 +47,7 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-extern int g_pdl;          // omt_set_option("pdl", 0|1)
-extern int g_f16_scheme;   // omt_set_option("f16_scheme", 1|2): format of the lo operand planes (gemm_f16.cu)
+extern int g_pdl;   // omt_set_option("pdl", 0|1)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -72,19 +71,17 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- fp16 hi / bf16 lo operand split of the f16x3 tensor-core path --------------------------------------------------
-// x ~= hi + lo with hi = fp16(x) (round to nearest, saturating at +-65504) and lo = bf16(x - hi): 11 + 8 significant
-// bits, the same representation error class as the tf32 hi/lo split (2^-21 |x|), but both halves are 16-bit operands
-// of kind::f16 MMAs (2x the tf32 rate, half the operand bytes).  bf16 keeps fp32's exponent range, so lo needs no
-// scaling and the three products  lo.hi + hi.lo + hi.hi  accumulate into ONE fp32 TMEM accumulator.
+// ---- fp16 hi / lo operand split of the f16x3 tensor-core path -----------------------------------------------------------
+// x ~= hi + lo * 2^-11 with hi = fp16(x) (round to nearest, saturating at +-65504) and lo = fp16((x - hi) * 2^11):
+// 11 + 11 significant bits, representation error <= 2^-23 |x| (tighter than the tf32 hi/lo split), and both halves are
+// 16-bit operands of kind::f16 MMAs (2x the tf32 rate, half the operand bytes).  The 2^11 keeps lo in fp16's normal
+// range for every |x| < 65504; the cross products  hi.lo + lo.hi  therefore carry a factor 2^11 and accumulate in their
+// own TMEM accumulator, folded in as  main + cross * 2^-11  by the epilogue.  (A bf16 lo plane would need no scaling and
+// a single accumulator, but a B200 raises "illegal instruction" on a kind::f16 MMA whose A and B formats differ.)
+constexpr float F16X3_LO_SCALE = 2048.0f;
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {   // {low half = a, high half = b}
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
 __device__ __forceinline__ float2 unpack_f16x2(uint32_t h) {
@@ -96,25 +93,19 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t h) {
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
   hi2 = pack_f16x2_sat(a, b);
   const float2 h = unpack_f16x2(hi2);
-  lo2 = pack_bf16x2(a - h.x, b - h.y);
-}
-// fallback operand format ("f16_scheme" 2): lo = fp16((x - hi) * 2^11), the cross products go to a second accumulator
-__device__ __forceinline__ void split2s(float a, float b, uint32_t& hi2, uint32_t& lo2, int scheme) {
-  hi2 = pack_f16x2_sat(a, b);
-  const float2 h = unpack_f16x2(hi2);
-  lo2 = scheme == 2 ? pack_f16x2_sat((a - h.x) * 2048.0f, (b - h.y) * 2048.0f) : pack_bf16x2(a - h.x, b - h.y);
+  lo2 = pack_f16x2_sat((a - h.x) * F16X3_LO_SCALE, (b - h.y) * F16X3_LO_SCALE);
 }
 // 4 consecutive values -> one 8-byte store per plane
-__device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, size_t off, float4 v, int scheme) {
+__device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, size_t off, float4 v) {
   uint2 h, l;
-  split2s(v.x, v.y, h.x, l.x, scheme);
-  split2s(v.z, v.w, h.y, l.y, scheme);
+  split2(v.x, v.y, h.x, l.x);
+  split2(v.z, v.w, h.y, l.y);
   *reinterpret_cast<uint2*>(hi + off) = h;
   *reinterpret_cast<uint2*>(lo + off) = l;
 }
-__device__ __forceinline__ void store_split2(uint16_t* hi, uint16_t* lo, size_t off, float2 v, int scheme) {
+__device__ __forceinline__ void store_split2(uint16_t* hi, uint16_t* lo, size_t off, float2 v) {
   uint32_t h, l;
-  split2s(v.x, v.y, h, l, scheme);
+  split2(v.x, v.y, h, l);
   *reinterpret_cast<uint32_t*>(hi + off) = h;
   *reinterpret_cast<uint32_t*>(lo + off) = l;
 }

@@ -49,7 +49,7 @@ int sm_count() {
 struct LnPlanes {          // optional fp16 hi / bf16 lo operand planes (omt_layernorm_h), written at the LOGICAL row
   uint16_t* y_hi; uint16_t* y_lo;    // normalised row
   uint16_t* x_hi; uint16_t* x_lo;    // raw input row (Attention.forward projects k, v from it)
-  int lds; int scheme;
+  int lds;
 };
 
 template <int NV>   // float4 chunks per lane
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (c < C) {
       v[i] = *reinterpret_cast<const float4*>(xr + c);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-      if (pl.x_hi != nullptr) store_split4(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i], pl.scheme);
+      if (pl.x_hi != nullptr) store_split4(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i]);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
       }
       if (y != nullptr) *reinterpret_cast<float4*>(yr + c) = o;
-      if (pl.y_hi != nullptr) store_split4(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, o, pl.scheme);
+      if (pl.y_hi != nullptr) store_split4(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, o);
     }
   }
 }
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <int NV>
 __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restrict__ video,
                                                           float* __restrict__ A, uint16_t* __restrict__ A_hi,
-                                                          uint16_t* __restrict__ A_lo, const int scheme,
+                                                          uint16_t* __restrict__ A_lo,
                                                           const float* __restrict__ lw,
                                                           const float* __restrict__ lb, int rows,
                                                           int Cin, int T, int H, int W, int p, int pt,
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
     for (int i = 0; i < NV; ++i) {
       const int f = (i * 32 + lane) * 4;
       if (f < K) {
-        if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, v[i], scheme);
+        if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, v[i]);
         else *reinterpret_cast<float4*>(A + rbase + f) = v[i];
       }
     }
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
       float4 o;
       o.x = v[i].x * rstd * g.x + bb.x; o.y = v[i].y * rstd * g.y + bb.y;
       o.z = v[i].z * rstd * g.z + bb.z; o.w = v[i].w * rstd * g.w + bb.w;
-      if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, o, scheme);
+      if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, o);
       else *reinterpret_cast<float4*>(A + rbase + f) = o;
     }
   }
@@ -213,6 +213,51 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict
     const int c = f / (p * p * PT);
     const size_t off = ((((size_t)bi * Cin + c) * T + (t0 + dt)) * H + (hi * p + p1)) * W + wi * p + p2;
     *reinterpret_cast<float4*>(video + off) = *reinterpret_cast<const float4*>(P + i * 4);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Un-patchify fused with the consumer's uint8 conversion (vqgan_eval.py:139,147-148; Latte sample_ddp.py:206;
+// DiT sample_ddp.py:163):  u8 = trunc( clamp(x * mul + add, lo, hi) * post )  written channels-LAST
+// (b, t, H, W, c) -- the layout every consumer permutes to before .byte().  mul / add / post are applied as separate
+// fp32 roundings (no fma contraction) so the bytes equal torch's elementwise expression on the fp32 reconstruction.
+// One thread = 4 consecutive pixels of one patch line, all Cin channels (Cin * 4 bytes contiguous in the output).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpatchify_u8_kernel(const float* __restrict__ P, uint8_t* __restrict__ out,
+                                                            long long total, int Cin, int T, int H, int W, int p,
+                                                            int pt, int first, float mul, float add, float lo,
+                                                            float hi, float post) {
+  pdl_sync();
+  const int hh = H / p, ww = W / p;
+  const int PT = first ? 1 : pt;
+  const int per_row = PT * p * (p / 4);           // (dt, p1, p2-quad) items per patch row
+  const int K = Cin * PT * p * p;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int it = (int)(i % per_row);
+    int r = (int)(i / per_row);
+    const int row = r;
+    const int q4 = it % (p / 4); it /= (p / 4);
+    const int p1 = it % p;
+    const int dt = it / p;
+    const int wi = r % ww; r /= ww;
+    const int hi_ = r % hh; r /= hh;
+    int ti = 0;
+    if (!first) { const int tn = (T - 1) / pt; ti = r % tn; r /= tn; }
+    const int bi = r;
+    const int t = first ? 0 : 1 + ti * pt + dt;
+    const size_t pix = (((size_t)bi * T + t) * H + (hi_ * p + p1)) * W + wi * p + q4 * 4;
+    uint8_t* o = out + pix * Cin;
+    for (int c = 0; c < Cin; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(P + (size_t)row * K + ((c * PT + dt) * p + p1) * p + q4 * 4);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float tv = __fadd_rn(__fmul_rn(e[j], mul), add);
+        tv = fminf(fmaxf(tv, lo), hi);
+        o[j * Cin + c] = (uint8_t)__float2uint_rz(__fmul_rn(tv, post));
+      }
+    }
   }
 }
 
@@ -596,14 +641,14 @@ extern "C" int omt_layernorm(const float* x, int ldx, float* y, int ldy, const f
                              int M, int C, float eps, int seg, int seg_stride, int seg_off,
                              omt_stream_t stream) {
   OMT_REQUIRE(y != nullptr, "omt_layernorm: null pointer");
-  omt::LnPlanes pl{nullptr, nullptr, nullptr, nullptr, 0, 1};
+  omt::LnPlanes pl{nullptr, nullptr, nullptr, nullptr, 0};
   return layernorm_impl("omt_layernorm", x, ldx, y, ldy, pl, w, b, M, C, eps, seg, seg_stride, seg_off, stream);
 }
 
 extern "C" int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, uint16_t* y_lo,
                                uint16_t* x_hi, uint16_t* x_lo, int lds, const float* w, const float* b,
                                int M, int C, float eps, int seg, int seg_stride, int seg_off, omt_stream_t stream) {
-  omt::LnPlanes pl{y_hi, y_lo, x_hi, x_lo, lds, omt::g_f16_scheme};
+  omt::LnPlanes pl{y_hi, y_lo, x_hi, x_lo, lds};
   return layernorm_impl("omt_layernorm_h", x, ldx, y, ldy, pl, w, b, M, C, eps, seg, seg_stride, seg_off, stream);
 }
 
@@ -614,7 +659,6 @@ extern "C" int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uin
   OMT_REQUIRE(video && (A || A_hi) && ((ln_w == nullptr) == (ln_b == nullptr)) && ((A_hi == nullptr) == (A_lo == nullptr)),
               "omt_patchify_ln: null pointer");
   OMT_REQUIRE(((uintptr_t)A_hi | (uintptr_t)A_lo) % 8 == 0, "omt_patchify_ln: planes must be 8-byte aligned");
-  const int scheme = omt::g_f16_scheme;
   OMT_REQUIRE(p % 4 == 0 && H % p == 0 && W % p == 0, "omt_patchify_ln: patch %d must be a multiple of 4 dividing %dx%d", p, H, W);
   OMT_REQUIRE(first || (T > 1 && (T - 1) % pt == 0), "omt_patchify_ln: (T-1) %% pt != 0");
   const int PT = first ? 1 : pt;
@@ -626,11 +670,11 @@ extern "C" int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uin
   dim3 grid((unsigned)((rows + 7) / 8)), block(256);
   const int nv = (K / 4 + 31) / 32;
   if (nv <= 2)
-    OMT_CUDA(launch_k(patchify_ln_kernel<2>, grid, block, 0, st, video, A, A_hi, A_lo, scheme, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<2>, grid, block, 0, st, video, A, A_hi, A_lo, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   else if (nv <= 6)
-    OMT_CUDA(launch_k(patchify_ln_kernel<6>, grid, block, 0, st, video, A, A_hi, A_lo, scheme, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<6>, grid, block, 0, st, video, A, A_hi, A_lo, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   else
-    OMT_CUDA(launch_k(patchify_ln_kernel<8>, grid, block, 0, st, video, A, A_hi, A_lo, scheme, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<8>, grid, block, 0, st, video, A, A_hi, A_lo, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -648,6 +692,25 @@ extern "C" int omt_unpatchify(const float* P, float* video, int B, int Cin, int 
   long long blocks = (total4 + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   OMT_CUDA(launch_k(unpatchify_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, P, video, total4, Cin, T, H, W, p, pt, first));
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
+extern "C" int omt_unpatchify_u8(const float* P, uint8_t* out, int B, int Cin, int T, int H, int W, int p, int pt,
+                                 int first, float mul, float add, float lo, float hi, float post, omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(P && out, "omt_unpatchify_u8: null pointer");
+  OMT_REQUIRE(p % 4 == 0 && H % p == 0 && W % p == 0, "omt_unpatchify_u8: bad patch size");
+  OMT_REQUIRE(first || (T > 1 && (T - 1) % pt == 0), "omt_unpatchify_u8: (T-1) %% pt != 0");
+  OMT_REQUIRE(lo >= 0.f && hi * post < 256.f, "omt_unpatchify_u8: clamp range [%g, %g] x %g does not fit a byte", lo, hi, post);
+  const int PT = first ? 1 : pt;
+  const long long rows = (long long)B * (first ? 1 : (T - 1) / pt) * (H / p) * (W / p);
+  const long long total = rows * PT * p * (p / 4);
+  if (total == 0) return OMT_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  OMT_CUDA(launch_k(unpatchify_u8_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, P, out, total, Cin, T, H, W, p,
+                    pt, first, mul, add, lo, hi, post));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -725,7 +788,7 @@ extern "C" int omt_qk_prep(float* q, int ldq, float* k, int ldk, const float* q_
   return OMT_OK;
 }
 
-namespace omt { extern int g_attn_kernel; }
+namespace omt { extern int g_attn_kernel; extern int g_f16_bn; }
 
 extern "C" int omt_set_option(const char* name, int value) {
   if (name == nullptr) return OMT_E_ARG;
@@ -740,9 +803,9 @@ extern "C" int omt_set_option(const char* name, int value) {
     omt::g_attn_kernel = value;
     return OMT_OK;
   }
-  if (strcmp(name, "f16_scheme") == 0) {
-    if (value != 1 && value != 2) { omt::set_error("f16_scheme must be 1 or 2"); return OMT_E_ARG; }
-    omt::g_f16_scheme = value;
+  if (strcmp(name, "f16_bn") == 0) {
+    if (value != 128 && value != 256) { omt::set_error("f16_bn must be 128 or 256"); return OMT_E_ARG; }
+    omt::g_f16_bn = value;
     return OMT_OK;
   }
   omt::set_error("unknown option %s", name);

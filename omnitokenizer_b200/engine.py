@@ -29,7 +29,7 @@ def default_math() -> str:
 
 
 class Planes:
-    """fp16 hi / bf16 lo operand planes of an [M, ld] fp32 matrix (the A operands of the f16x3 GEMMs)."""
+    """fp16 hi / lo operand planes of an [M, ld] fp32 matrix (the A operands of the f16x3 GEMMs; layout.split_f16)."""
 
     def __init__(self, device, M: int, ld: int):
         self.buf = torch.empty(2, M, ld, device=device, dtype=torch.int16)
@@ -40,7 +40,7 @@ class PackedLinear:
     """nn.Linear weight in GEMM layout: rows padded to 128, K padded, optional tf32 hi/lo split."""
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], device, math: int,
-                 k_pad: Optional[int] = None, geglu: Optional[Tuple[int, int]] = None, scheme: int = 1):
+                 k_pad: Optional[int] = None, geglu: Optional[Tuple[int, int]] = None):
         w = weight.detach().to(device=device, dtype=torch.float32)
         if geglu is not None:
             inner, ku = geglu
@@ -54,7 +54,7 @@ class PackedLinear:
             hi = L.tf32_round(w)
             self.w, self.w_lo = hi, (w - hi).contiguous()
         elif math == _cabi.MATH_F16X3:
-            self.w, self.w_lo = L.split_f16(w, scheme)          # 16-bit operand planes
+            self.w, self.w_lo = L.split_f16(w)          # fp16 operand planes
         else:
             self.w, self.w_lo = w, None
         self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -70,7 +70,7 @@ class Workspace:
         self.X, self.Y = self.buf0, self.buf1
         self.QKV = torch.empty(M, 3 * C, **f)
         self.P = torch.empty(M, kmax, **f)       # patch matrix (pixels side), rows x K
-        if planes:     # f16x3: every GEMM A operand lives as fp16 hi / bf16 lo planes written by its producer
+        if planes:     # f16x3: every GEMM A operand lives as fp16 hi / lo planes written by its producer
             self.XNp, self.XSp, self.Op = Planes(device, M, C), Planes(device, M, C), Planes(device, M, C)
             self.Up, self.Pp = Planes(device, M, ku), Planes(device, M, kmax)
         else:
@@ -83,6 +83,7 @@ class Workspace:
         self.vqws = torch.empty(4 * M * 2, **f)
         # static I/O buffers + captured CUDA graphs of this shape
         self.x_in = None
+        self.video_u8 = None
         self.idx_in = torch.empty(M, device=device, dtype=torch.int64)
         self.zc_in = torch.empty(M, cd, **f)
         self.zq = torch.empty(M, cd, **f)
@@ -99,8 +100,8 @@ class Engine:
         _cabi.set_option("pdl", int(os.environ.get("OMT_PDL", "0")))     # programmatic dependent launch between kernels
         if os.environ.get("OMT_PEG_KERNEL"):                             # 3 | 4, tuning knob (default: the library's)
             _cabi.set_option("peg_kernel", int(os.environ["OMT_PEG_KERNEL"]))
-        self.scheme = int(os.environ.get("OMT_F16_SCHEME", "1"))         # format of the f16x3 lo planes (see the C header)
-        _cabi.set_option("f16_scheme", self.scheme)
+        if os.environ.get("OMT_F16_BN"):                                 # 128 | 256, tile N of the f16x3 GEMM (tuning knob)
+            _cabi.set_option("f16_bn", int(os.environ["OMT_F16_BN"]))
         self.device = device
         self.math_name = (math or default_math()).lower()
         if self.math_name not in MATH_MODES:
@@ -138,7 +139,7 @@ class Engine:
         self.ku = L.round_up(self.inner, 64 if self.planes else 32)     # K of the second FF GEMM: whole k-blocks
 
         def PL(weight, bias, **kw):
-            return PackedLinear(weight, bias, dev, m, scheme=self.scheme, **kw)
+            return PackedLinear(weight, bias, dev, m, **kw)
 
         def lin(name, bias=True, **kw):
             return PL(sd[name + ".weight"], sd.get(name + ".bias") if bias else None, **kw)
@@ -453,8 +454,9 @@ class Engine:
         return self._dense(ws.zq, ws.M, self.post_w.shape[1])
 
     # ------------------------------------------------------------------ decoder side
-    def _decode_body(self, ws: Workspace, dims, mode: str):
-        """[gather +] post_vq -> temporal -> spatial -> to_pixels.  omnitokenizer.py:268-317, 1059-1118."""
+    def _decode_body(self, ws: Workspace, dims, mode: str, u8=None):
+        """[gather +] post_vq -> temporal -> spatial -> to_pixels.  omnitokenizer.py:268-317, 1059-1118.
+        u8 = (mul, add, lo, hi, post): the pixels leave as uint8 (B,T,H,W,C) = trunc(clamp(x*mul+add, lo, hi)*post)."""
         B, Tp, h, w = dims
         N, M, C = h * w, ws.M, self.C
         ws.reset()
@@ -478,21 +480,26 @@ class Engine:
                 self._linear_h(ws.XNp, px, rows, C=ws.P, ldc=K, a_map=amap)
             else:
                 self._linear(ws.X, C, px, ws.P, K, rows, a_map=amap)
-            _cabi.call("omt_unpatchify", ws.P, ws.video, B, self.cin, T, H, W, self.p, self.pt, first)
+            if u8 is None:
+                _cabi.call("omt_unpatchify", ws.P, ws.video, B, self.cin, T, H, W, self.p, self.pt, first)
+            else:
+                _cabi.call("omt_unpatchify_u8", ws.P, ws.video_u8, B, self.cin, T, H, W, self.p, self.pt, first, *u8)
 
         pixels(self.px["first"], 1, B * N, k1, (N, Tp * N, 0))
         if Tp > 1:
             pixels(self.px["rest"], 0, B * (Tp - 1) * N, k1 * self.pt, ((Tp - 1) * N, Tp * N, N))
 
-    def decode(self, dims, *, idx=None, zc=None, straight_through=False) -> torch.Tensor:
+    def decode(self, dims, *, idx=None, zc=None, straight_through=False, u8=None) -> torch.Tensor:
         """dims (B,T',h,w).  idx: int64 [M] codes | zc: fp32 [M, cd] latents (VAE).  With straight_through
         the rows are (E[idx] - z) + z using the z left in the workspace by encode(); ws.zq receives them.
-        Returns a fresh (B,C,T,H,W) tensor (the reference's decoder ends in .clone(), omnitokenizer.py:1116)."""
+        Returns a fresh (B,C,T,H,W) tensor (the reference's decoder ends in .clone(), omnitokenizer.py:1116);
+        with u8 = (mul, add, lo, hi, post) a fresh uint8 (B,T,H,W,C) tensor (fused consumer conversion)."""
         B, Tp, h, w = dims
         ws = self._workspace(B * Tp * h * w)
         vshape = (B, self.cin, 1 + (Tp - 1) * self.pt, h * self.p, w * self.p)
         if ws.video is None or tuple(ws.video.shape) != vshape:
             ws.video = torch.empty(vshape, device=self.device, dtype=torch.float32)
+            ws.video_u8 = torch.empty((B, vshape[2], vshape[3], vshape[4], self.cin), device=self.device, dtype=torch.uint8)
             ws.graphs = {k: v for k, v in ws.graphs.items() if not k[0].startswith("dec")}
         if idx is not None:
             ws.idx_in.copy_(idx.reshape(-1))
@@ -500,5 +507,6 @@ class Engine:
         else:
             self._dense(ws.zc_in, ws.M, zc.shape[1]).copy_(zc)
             mode = "zc"
-        self._run(ws, ("dec:" + mode, dims), lambda: self._decode_body(ws, dims, mode))
-        return ws.video.clone()
+        u8 = None if u8 is None else tuple(float(v) for v in u8)
+        self._run(ws, ("dec:" + mode, dims, u8), lambda: self._decode_body(ws, dims, mode, u8))
+        return ws.video.clone() if u8 is None else ws.video_u8.clone()

@@ -72,14 +72,21 @@ def tf32_round(w: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & -8192).view(torch.float32)
 
 
-def split_f16(w: torch.Tensor, scheme: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+F16X3_LO_SCALE = 2048.0
+
+
+def split_f16(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Operand planes of the f16x3 tensor-core path (csrc/omt_common.cuh): hi = fp16(w) (round to nearest, saturating)
-    and lo = bf16(w - hi); scheme 2: lo = fp16((w - hi) * 2^11).  Same rounding as the device-side split."""
+    and lo = fp16((w - hi) * 2^11); w ~= hi + lo * 2^-11 to 2^-23 |w|.  Same rounding as the device-side split."""
     w = w.float()
     hi = w.clamp(-65504.0, 65504.0).to(torch.float16)
-    r = w - hi.float()
-    lo = r.to(torch.bfloat16) if scheme == 1 else (r * 2048.0).clamp(-65504.0, 65504.0).to(torch.float16)
+    lo = ((w - hi.float()) * F16X3_LO_SCALE).clamp(-65504.0, 65504.0).to(torch.float16)
     return hi.contiguous(), lo.contiguous()
+
+
+def join_f16(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
+    """fp32 value a pair of operand planes stands for (int16 views are reinterpreted as fp16)."""
+    return hi.view(torch.float16).float() + lo.view(torch.float16).float() / F16X3_LO_SCALE
 
 
 def pad_rows(w: torch.Tensor, mult: int) -> torch.Tensor:

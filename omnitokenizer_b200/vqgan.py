@@ -354,52 +354,72 @@ class OmniTokenizer_VQGAN(nn.Module):
             raise ValueError(f"patch_embed='cnn' decodes only the configured resolution ({self.resolution}): "
                              f"token grid {h}x{w} != {self.resolution // self.patch_size}")
 
-    @torch.no_grad()
-    def decode(self, encodings, is_image):
-        """omnitokenizer.py:268-317 (index / flat-index / VAE 4-D 'b c h w' / 5-D 'b t h w c' conventions)."""
-        eng = self.engine()
-        with torch.cuda.device(self.device):
-            if not self.use_vae:
-                enc = encodings
-                if enc.ndim == 2:
-                    B = enc.shape[0]
-                    if is_image:
-                        h = w = int(math.sqrt(enc.shape[1])); Tp = 1
-                    else:
-                        h = w = self.resolution // self.patch_size; Tp = enc.shape[1] // (h * w)
-                elif enc.ndim == 3 and is_image:                                   # (B, h, w) is not a reference form
-                    raise ValueError("image indices must be (B, h*w) or (B, 1, h, w)")
+    def _decode_inputs(self, encodings, is_image):
+        """The index / flat-index / VAE 4-D 'b c h w' / 5-D 'b t h w c' conventions of omnitokenizer.py:268-317
+        -> (dims (B,T',h,w), idx [M] | None, zc [M, cd] | None)."""
+        if not self.use_vae:
+            enc = encodings
+            if enc.ndim == 2:
+                B = enc.shape[0]
+                if is_image:
+                    h = w = int(math.sqrt(enc.shape[1])); Tp = 1
                 else:
-                    B, Tp, h, w = enc.shape
-                self._check_cnn_grid(h, w)
-                idx = enc.reshape(-1).to(device=self.device, dtype=torch.int64)
-                if B == 0:
-                    T = 1 + (Tp - 1) * self.args.temporal_patch_size
-                    video = torch.empty((0, self.args.image_channels, T, h * self.patch_size, w * self.patch_size), device=self.device)
-                    return video.squeeze(2) if is_image else video
+                    h = w = self.resolution // self.patch_size; Tp = enc.shape[1] // (h * w)
+            elif enc.ndim == 3 and is_image:                                   # (B, h, w) is not a reference form
+                raise ValueError("image indices must be (B, h*w) or (B, 1, h, w)")
+            else:
+                B, Tp, h, w = enc.shape
+            self._check_cnn_grid(h, w)
+            idx = enc.reshape(-1).to(device=self.device, dtype=torch.int64)
+            if B > 0:
                 # F.embedding device-asserts on out-of-range indices (omnitokenizer.py:270); same here, without a host sync
                 torch._assert_async(((idx >= 0) & (idx < self.codebook.n_codes)).all(),
                                     "decode: code index out of range [0, n_codes)")
-                video = eng.decode((B, Tp, h, w), idx=idx)
+            return (B, Tp, h, w), idx, None
+        z = encodings.to(device=self.device, dtype=torch.float32)
+        if is_image:
+            if z.ndim == 3:
+                B = z.shape[0]; h = w = int(math.sqrt(z.shape[1])); Tp = 1
+                zc = z.reshape(B * h * w, -1)
             else:
-                z = encodings.to(device=self.device, dtype=torch.float32)
-                if is_image:
-                    if z.ndim == 3:
-                        B = z.shape[0]; h = w = int(math.sqrt(z.shape[1])); Tp = 1
-                        zc = z.reshape(B * h * w, -1)
-                    else:
-                        B, c, h, w = z.shape; Tp = 1
-                        zc = z.permute(0, 2, 3, 1).reshape(B * h * w, c)
-                else:
-                    if z.ndim == 3:
-                        B = z.shape[0]; h = w = self.resolution // self.patch_size; Tp = z.shape[1] // (h * w)
-                        zc = z.reshape(B * Tp * h * w, -1)
-                    else:
-                        B, Tp, h, w, c = z.shape
-                        zc = z.reshape(B * Tp * h * w, c)
-                self._check_cnn_grid(h, w)
-                video = eng.decode((B, Tp, h, w), zc=zc)
-            return video.squeeze(2) if is_image else video
+                B, c, h, w = z.shape; Tp = 1
+                zc = z.permute(0, 2, 3, 1).reshape(B * h * w, c)
+        else:
+            if z.ndim == 3:
+                B = z.shape[0]; h = w = self.resolution // self.patch_size; Tp = z.shape[1] // (h * w)
+                zc = z.reshape(B * Tp * h * w, -1)
+            else:
+                B, Tp, h, w, c = z.shape
+                zc = z.reshape(B * Tp * h * w, c)
+        self._check_cnn_grid(h, w)
+        return (B, Tp, h, w), None, zc
+
+    def _decode(self, encodings, is_image, u8=None):
+        eng = self.engine()
+        with torch.cuda.device(self.device):
+            dims, idx, zc = self._decode_inputs(encodings, is_image)
+            B, Tp, h, w = dims
+            if B == 0:
+                T, H, W = 1 + (Tp - 1) * self.args.temporal_patch_size, h * self.patch_size, w * self.patch_size
+                if u8 is not None:
+                    return torch.empty((0, T, H, W, self.args.image_channels), dtype=torch.uint8, device=self.device)
+                video = torch.empty((0, self.args.image_channels, T, H, W), device=self.device)
+                return video.squeeze(2) if is_image else video
+            return eng.decode(dims, idx=idx, zc=zc, u8=u8)
+
+    @torch.no_grad()
+    def decode(self, encodings, is_image):
+        """omnitokenizer.py:268-317 (index / flat-index / VAE 4-D 'b c h w' / 5-D 'b t h w c' conventions)."""
+        video = self._decode(encodings, is_image)
+        return video.squeeze(2) if is_image else video
+
+    @torch.no_grad()
+    def decode_u8(self, encodings, is_image, affine=(1.0, 0.5, 0.0, 1.0, 255.0)):
+        """decode() fused with the consumers' uint8 conversion: returns (B, T, H, W, C) uint8 (T = 1 for images) =
+        trunc(clamp(x * mul + add, lo, hi) * post), bit-identical to the torch expression on decode()'s result.
+        Default affine: vqgan_eval.py:139,147-148 `(clamp(x_recons + 0.5, 0, 1) * 255).byte()` in 'b t h w c' order;
+        (255, 128, 0, 255, 1): DiT sample_ddp.py:163.  The device->host copy is 4x smaller than the fp32 video."""
+        return self._decode(encodings, is_image, u8=affine)
 
     @torch.no_grad()
     def forward(self, x, optimizer_idx=None, log_image=False):

@@ -24,12 +24,12 @@ def timeit(fn, reps=7):
 
 
 SHAPES = [("qkv", 1536, 512, "qkv"), ("out+res", 512, 512, "res"), ("ff1+geglu", 2730, 512, "geglu"), ("ff2+res", 512, 1365, "res")]
-for scheme in ([1, 2] if os.environ.get("BOTH_SCHEMES") else [1]):
-  _cabi.set_option("f16_scheme", scheme)
+for scheme in [int(v) for v in os.environ.get("F16_BN", "256,128").split(",")]:
+  _cabi.set_option("f16_bn", scheme)
   for M in Ms:
     for name, N, K, kind in SHAPES:
         g = torch.Generator(device=dev).manual_seed(1)
-        for math in ("3xtf32", "f16x3"):
+        for math in (("3xtf32", "f16x3") if scheme == 256 else ("f16x3",)):
             mult = 64 if math == "f16x3" else 32
             if kind == "geglu":
                 inner = 1365; ku = L.round_up(inner, mult); Np = 2 * ku; Kp = K
@@ -51,7 +51,7 @@ for scheme in ([1, 2] if os.environ.get("BOTH_SCHEMES") else [1]):
                 else:
                     fn = lambda: _cabi.call("omt_linear", A, Kp, 0, 0, 0, hi, lo, R, 512, 0, 0, 0, M, Np, Kp, None, R, 512, _cabi.EPI_NONE, _cabi.MATH_3XTF32)
             else:
-                ah, al = L.split_f16(A, scheme); wh, wl = L.split_f16(L.pad_rows(W, 256), scheme)
+                ah, al = L.split_f16(A); wh, wl = L.split_f16(L.pad_rows(W, 256))
                 if kind == "geglu":
                     U = torch.empty(2, M, Np // 2, dtype=torch.int16, device=dev)
                     fn = lambda: _cabi.linear_h(a_hi=ah, a_lo=al, lda=Kp, w_hi=wh, w_lo=wl, u_hi=U[0], u_lo=U[1], ldu=Np // 2, M=M, N=Np, K=Kp, epilogue=_cabi.EPI_GEGLU)
@@ -63,7 +63,7 @@ for scheme in ([1, 2] if os.environ.get("BOTH_SCHEMES") else [1]):
             try:
                 us = timeit(fn)
                 tf = flops / us / 1e6
-                print(f"scheme{scheme} M={M:6d} {name:10s} {math:7s} {us:8.1f} us  {tf:7.1f} TFLOP/s  {tf / pk:.3f} of tf32 peak", flush=True)
+                print(f"bn{scheme} M={M:6d} {name:10s} {math:7s} {us:8.1f} us  {tf:7.1f} TFLOP/s  {tf / pk:.3f} of tf32 peak", flush=True)
             except Exception as e:
-                print(f"scheme{scheme} M={M} {name} {math} FAILED: {e}", flush=True)
+                print(f"bn{scheme} M={M} {name} {math} FAILED: {e}", flush=True)
                 raise

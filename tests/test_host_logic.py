@@ -16,10 +16,14 @@ class _StubEngine:
         self.p, self.pt, self.cin = a.patch_size, a.temporal_patch_size, a.image_channels
         self.calls = []
 
-    def decode(self, dims, *, idx=None, zc=None, straight_through=False):
+    def decode(self, dims, *, idx=None, zc=None, straight_through=False, u8=None):
         B, Tp, h, w = dims
-        self.calls.append(dict(dims=dims, idx=None if idx is None else idx.clone(), zc=None if zc is None else zc.clone()))
-        return torch.zeros(B, self.cin, 1 + (Tp - 1) * self.pt, h * self.p, w * self.p)
+        self.calls.append(dict(dims=dims, idx=None if idx is None else idx.clone(), zc=None if zc is None else zc.clone(),
+                               u8=u8))
+        T = 1 + (Tp - 1) * self.pt
+        if u8 is not None:
+            return torch.zeros(B, T, h * self.p, w * self.p, self.cin, dtype=torch.uint8)
+        return torch.zeros(B, self.cin, T, h * self.p, w * self.p)
 
 
 def _model(extra=()):
@@ -53,6 +57,10 @@ def test_decode_index_conventions():
     assert stub.calls[-1]["dims"] == (3, 1, 8, 8) and tuple(out.shape) == (3, 3, 64, 64)
     out = m.decode(torch.randint(0, 8192, (3, 1, 16, 16)), True)
     assert tuple(out.shape) == (3, 3, 128, 128)
+    # fused uint8 form: same conventions, channels-last bytes, the eval script's affine by default
+    out = m.decode_u8(codes.reshape(2, -1), False)
+    assert stub.calls[-1]["dims"] == (2, 5, 32, 32) and stub.calls[-1]["u8"] == (1.0, 0.5, 0.0, 1.0, 255.0)
+    assert tuple(out.shape) == (2, 17, 256, 256, 3) and out.dtype == torch.uint8
 
 
 def test_decode_vae_layouts():
@@ -88,23 +96,17 @@ def test_unsupported_configurations_say_why():
     assert m.args.attn_dropout == 0.1
 
 
-def _join(hi, lo, scheme):
-    if scheme == 1:
-        return hi.view(torch.float16).float() + lo.view(torch.bfloat16).float()
-    return hi.view(torch.float16).float() + lo.view(torch.float16).float() / 2048.0
-
-
 def test_f16x3_split_is_tight():
     """Host-side operand split of the f16x3 path (layout.split_f16 == the device-side rule in csrc/omt_common.cuh):
-    |x - (hi + lo)| <= 2^-20 |x| with bf16 lo planes (scheme 1), 2^-22 |x| with scaled fp16 lo planes (scheme 2);
-    hi saturates instead of overflowing and lo carries the remainder."""
+    |x - (hi + lo * 2^-11)| <= 2^-22 |x|; hi saturates instead of overflowing and lo carries what it can of the rest."""
     from omnitokenizer_b200 import layout as L
     x = (torch.rand(4096, generator=torch.Generator().manual_seed(1)) - 0.5) * 60.0
-    for scheme, bound in ((1, 2.0 ** -20), (2, 2.0 ** -22)):
-        hi, lo = L.split_f16(x, scheme)
-        assert hi.dtype == torch.float16 and lo.dtype == (torch.bfloat16 if scheme == 1 else torch.float16)
-        assert ((_join(hi, lo, scheme) - x).abs() <= bound * x.abs() + 1e-30).all()
-    big = torch.tensor([1e6, -3e5, 65504.0, 7e-8])
-    hi, lo = L.split_f16(big, 1)
-    assert torch.isfinite(hi.float()).all() and torch.isfinite(lo.float()).all()
-    assert (_join(hi, lo, 1) - big).abs().max() < 4e3            # 8 significant bits left above the fp16 range
+    hi, lo = L.split_f16(x)
+    assert hi.dtype == torch.float16 and lo.dtype == torch.float16
+    assert ((L.join_f16(hi, lo) - x).abs() <= 2.0 ** -22 * x.abs() + 1e-30).all()
+    tiny = torch.tensor([3e-6, -7e-8, 1e-9])                    # below fp16's normal range: lo rescues the precision
+    hi, lo = L.split_f16(tiny)
+    assert ((L.join_f16(hi, lo) - tiny).abs() <= 2.0 ** -36).all()
+    big = torch.tensor([1e6, -3e5, 65504.0])
+    hi, lo = L.split_f16(big)
+    assert torch.isfinite(hi.float()).all() and torch.isfinite(lo.float()).all()        # saturates, never inf / nan
