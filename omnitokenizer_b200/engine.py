@@ -21,7 +21,7 @@ from . import _cabi
 from . import layout as L
 
 MATH_MODES = {"fp32": _cabi.MATH_FP32, "3xtf32": _cabi.MATH_3XTF32, "f16x3": _cabi.MATH_F16X3}
-DEFAULT_MATH = "3xtf32"
+DEFAULT_MATH = "f16x3"
 
 
 def default_math() -> str:

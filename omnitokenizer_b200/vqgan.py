@@ -16,6 +16,7 @@ vqgan_eval.py:62-71 already loads.
 from __future__ import annotations
 
 import argparse
+import random
 import math
 from typing import Optional
 
@@ -227,10 +228,10 @@ class OmniTokenizer_VQGAN(nn.Module):
         self.resolution = args.resolution
         self.patch_size = args.patch_size
         self.resolution_scale = args.resolution_scale
-        if args.defer_temporal_pool or args.defer_spatial_pool or args.gen_upscale is not None or \
-                args.resolution_scale is not None:
-            raise NotImplementedError("defer_*_pool / gen_upscale / resolution_scale are multi-resolution training options "
-                                      "outside the encode/decode hot path (SURVEY.md 8f.4)")
+        if args.defer_temporal_pool or args.defer_spatial_pool or args.gen_upscale is not None:
+            raise NotImplementedError("defer_*_pool / gen_upscale are multi-resolution training options that change the "
+                                      "architecture (pooling / upsampling blocks), outside the encode/decode hot path "
+                                      "(SURVEY.md 8f.4)")
         if args.use_external_codebook:
             raise NotImplementedError("--use_external_codebook (vendored lucidrains quantizers) is never set by the shipped "
                                       "scripts and is out of scope")
@@ -430,6 +431,14 @@ class OmniTokenizer_VQGAN(nn.Module):
                                       "training step is out of scope")
         eng = self.engine()
         is_image = x.ndim == 4
+        if self.resolution_scale is not None:
+            # multi-resolution option (omnitokenizer.py:334-355): ONE random.choices draw per call picks the scale, every
+            # frame is resized bilinearly (align_corners=True) before the encoder; x is returned at that resolution
+            scale = random.choices(self.resolution_scale)[0]
+            side = int(x.shape[-2] * scale)
+            flat = x if is_image else x.permute(0, 2, 1, 3, 4).reshape(-1, x.shape[1], x.shape[3], x.shape[4])
+            flat = torch.nn.functional.interpolate(flat.float(), size=(side, side), mode="bilinear", align_corners=True)
+            x = flat if is_image else flat.reshape(x.shape[0], x.shape[2], x.shape[1], side, side).permute(0, 2, 1, 3, 4).contiguous()
         with torch.cuda.device(self.device):
             xv = (x.unsqueeze(2) if is_image else x).float()
             ws, dims = eng.encode(xv, "raw" if self.use_vae else "vq")

@@ -531,3 +531,47 @@ def forward_log_image(sd: SD, cfg: Config, x: Tensor, frame_idx: Optional[Tensor
         ar = torch.arange(B)
         frames, frames_recon = x[ar, :, frame_idx], x_recon[ar, :, frame_idx]
     return frames, frames_recon, x, x_recon, vq_output
+
+
+# ---- consumers either side of encode / decode -----------------------------------------------------
+LATENT_SCALE = 0.18215
+
+
+def to_u8(video: Tensor, mul: float = 1.0, add: float = 0.5, lo: float = 0.0, hi: float = 1.0, post: float = 255.0) -> Tensor:
+    """(B,C,T,H,W) fp32 -> (B,T,H,W,C) uint8.  Defaults: vqgan_eval.py:139,147-148  shift_dim(clamp(x + 0.5, 0, 1) * 255, 1, -1)
+    .byte()  (also Latte sample_ddp.py:206); (255, 128, 0, 255, 1): DiT sample_ddp.py:163  clamp(255 * x + 128.0, 0, 255)."""
+    t = torch.clamp(video * mul + add, lo, hi) * post
+    return t.permute(0, 2, 3, 4, 1).contiguous().to(torch.uint8)
+
+
+def encode_to_z(sd: SD, cfg: Config, x: Tensor, is_image: bool, sample_every_n_latent_frames: int = 0):
+    """lm_transformer.py:258-268 (vtokens False): embeddings channels-last + flat targets, every n-th latent frame."""
+    emb, targets = encode(sd, cfg, x, include_embeddings=True)
+    if sample_every_n_latent_frames > 0:
+        emb = emb[:, :, ::sample_every_n_latent_frames]
+        targets = targets[:, ::sample_every_n_latent_frames]
+    return emb.permute(0, 2, 3, 4, 1).contiguous(), targets.reshape(targets.shape[0], -1)
+
+
+def decode_tokens(sd: SD, cfg: Config, ix: Tensor, is_image: bool, cond_stage_vocab_size: int = 0) -> Tensor:
+    """lm_transformer.py:433-434: clamp(ix - cond_vocab, 0, first_vocab - 1).squeeze(-1) -> decode (flat indices)."""
+    n_codes = sd["codebook.embeddings"].shape[0]
+    index = torch.clamp(ix - cond_stage_vocab_size, min=0, max=n_codes - 1)
+    if index.ndim == 3:
+        index = index.squeeze(-1)
+    return decode(sd, cfg, index, is_image)
+
+
+def dit_roundtrip(sd: SD, cfg: Config, x: Tensor, noise: Tensor):
+    """DiT/train.py:242 then DiT/sample_ddp.py:162-163 on the same latent: (scaled latents, uint8 images (B,H,W,3))."""
+    z = encode(sd, cfg, x, noise=noise) * LATENT_SCALE
+    img = decode(sd, cfg, z / LATENT_SCALE, True)
+    return z, to_u8(img.unsqueeze(2), 255.0, 128.0, 0.0, 255.0, 1.0)[:, 0]
+
+
+def latte_roundtrip(sd: SD, cfg: Config, x_bfchw: Tensor, noise: Tensor):
+    """Latte/train.py:215-217 then sample_ddp.py:201-206: (scaled latents 'b f c h w', video 'b f c h w', uint8 'b f h w c')."""
+    z = encode(sd, cfg, x_bfchw.permute(0, 2, 1, 3, 4).contiguous(), noise=noise) * LATENT_SCALE
+    z = z.permute(0, 2, 1, 3, 4).contiguous()
+    video = decode(sd, cfg, z.permute(0, 1, 3, 4, 2) / LATENT_SCALE, False)
+    return z, video.permute(0, 2, 1, 3, 4).contiguous(), to_u8(video)

@@ -158,3 +158,48 @@ def test_3xtf32_numerics_model_keeps_code_indices(name, monkeypatch):
     assert err["3xtf32"][0] == 0, f"3xTF32 model flipped {err['3xtf32'][0]} indices"
     assert err["3xtf32"][1] <= 1e-4, err
     assert err["tf32"][1] > 20 * err["3xtf32"][1], err                 # the single-pass mode is far off fp32 grade
+
+
+@pytest.mark.reference
+def test_consumer_restatements_match_live_reference():
+    """Net2NetTransformer.encode_to_z (lm_transformer.py:258-268) run UNBOUND on a stub carrying the live
+    reference VQGAN, against the oracle's restatement; plus shift_dim / the eval script's uint8 expression."""
+    from oracle import ref_loader as rl
+    if not rl.available():
+        pytest.skip("reference tree not present")
+    import types
+    ref, args = rl.make_model(seed=3)
+    import OmniTokenizer.lm_transformer as lt
+    from OmniTokenizer.utils import shift_dim
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    cfg = oo.Config()
+    x = W.synthetic_input((1, 3, 9, 64, 64), 55)
+    for n in (0, 2):
+        stub = types.SimpleNamespace(vtokens=False, first_stage_model=ref, sample_every_n_latent_frames=n)
+        with torch.no_grad():
+            emb_r, tgt_r = lt.Net2NetTransformer.encode_to_z(stub, x, False)
+            emb_o, tgt_o = oo.encode_to_z(sd, cfg, x, False, n)
+        assert torch.equal(tgt_r, tgt_o) and (emb_r - emb_o).abs().max().item() < 1e-5
+    v = torch.rand(2, 3, 5, 8, 8) - 0.5
+    assert torch.equal(shift_dim(torch.clamp(v + 0.5, 0, 1) * 255, 1, -1).byte(), oo.to_u8(v))
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("strategy", ["average", "first"])
+def test_inflate_gen_matches_live_reference(strategy):
+    """Checkpoint tooling: omnitokenizer_b200.ckpt.inflate_gen vs OmniTokenizer/utils.py:11 on a synthetic
+    checkpoint, key for key and bit for bit; the inflated checkpoint then loads into the module without missing keys."""
+    from oracle import ref_loader as rl
+    if not rl.available():
+        pytest.skip("reference tree not present")
+    rl.load()
+    from OmniTokenizer.utils import inflate_gen as ref_inflate
+    import omnitokenizer_b200 as ob
+    from omnitokenizer_b200.ckpt import inflate_gen
+    sd = W.make_state_dict(oo.Config(), 4)
+    a, b = inflate_gen(sd, 4, 8, strategy), ref_inflate(sd, 4, 8, strategy=strategy)
+    assert a.keys() == b.keys()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    m = ob.OmniTokenizer_VQGAN(ob.canonical_args())
+    res = m.load_state_dict(a, strict=False)
+    assert not res.missing_keys
