@@ -90,8 +90,9 @@ int omt_layernorm(const float* x, int ldx, float* y, int ldy, const float* w, co
  * video (B, Cin, T, H, W) fp32 contiguous.  first=1: frame 0, rows (b,h,w), features (c,p1,p2);
  * first=0: frames 1.., rows (b,t,h,w), features (c,pt,p1,p2).  A is [rows, K] dense.
  * ln_w == ln_b == NULL: plain patch gather (im2col of the strided Conv3d of patch_embed='cnn', omnitokenizer.py:823-838).
- * A_hi != NULL: the rows are written as fp16 hi / lo operand planes [rows, K] instead of A (A may be NULL). */
-int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uint16_t* A_lo, const float* ln_w, const float* ln_b,
+ * A_hi != NULL: the rows are written as fp16 hi / lo operand planes [rows, K] instead of A (A may be NULL);
+ * A_rs != NULL: in the row-scaled form, inverse row scales to A_rs [rows]. */
+int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uint16_t* A_lo, float* A_rs, const float* ln_w, const float* ln_b,
                     int B, int Cin, int T, int H, int W, int p, int pt, int first, float eps,
                     omt_stream_t stream);
 
@@ -171,9 +172,15 @@ int omt_post_vq(const int64_t* idx, const float* E, const float* zc, const float
 /* ---- f16x3 path: operands as 16-bit planes ------------------------------------------------------------
  * An fp32 matrix X is carried as hi = fp16(X) (round to nearest, saturating) and lo = fp16((X - hi) * 2^11), two
  * uint16 matrices with a common leading dimension: X ~= hi + lo * 2^-11 to 2^-23 |X| for |X| < 65504.
- * Producers below write the planes directly; weights are split once on the host. */
+ * Producers below write the planes directly; weights are split once on the host.
+ * ROW-SCALED form: a producer that sees whole rows (LayerNorm, patch gather) multiplies the row by the power of two
+ * that puts its largest magnitude in [2^14, 2^15) and stores hi = fp16(x'), lo = fp16(x' - hi) UNSCALED plus the inverse
+ * scale per row; the weights carry one such scale per matrix.  The GEMM then needs ONE accumulator instead of two
+ * (256-wide tiles AND double buffering).  Both A operands of a dual-A call use the same form. */
 typedef struct omt_linear_h_args {
   const uint16_t* a_hi; const uint16_t* a_lo;      /* A planes [M, lda] */
+  const float* a_rs; const float* a2_rs;           /* non-NULL: ROW-SCALED planes (below): inverse row scales [rows of A] */
+  float w_scale;                                   /* row-scaled form: inverse of the per-matrix scale of the W planes */
   const uint16_t* a2_hi; const uint16_t* a2_lo;    /* optional second A (dual-A form, columns >= n_split), same lda / row map */
   int n_split;                                     /* multiple of 256 */
   int lda, a_seg, a_seg_stride, a_seg_off;         /* lda % 8 == 0; row map as in omt_linear (segments of 64 rows) */
@@ -193,16 +200,17 @@ int omt_linear_h(const omt_linear_h_args* args, omt_stream_t stream);
 /* LayerNorm as omt_layernorm with plane outputs for the GEMM that consumes it:
  * y (fp32, may be NULL), (y_hi, y_lo) planes of the normalised row, and optionally (x_hi, x_lo) planes of the RAW
  * input row -- Attention.forward projects k, v from the un-normalised input (attention.py:407-412).  lds = leading
- * dimension of every plane (lds % 8 == 0).  The row map applies to x / y; planes are written at the LOGICAL row. */
-int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, uint16_t* y_lo,
-                    uint16_t* x_hi, uint16_t* x_lo, int lds, const float* w, const float* b,
+ * dimension of every plane (lds % 8 == 0).  The row map applies to x / y; planes are written at the LOGICAL row.
+ * y_rs / x_rs != NULL: that plane pair is written in the row-scaled form and the inverse row scales go to y_rs / x_rs [M]. */
+int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, uint16_t* y_lo, float* y_rs,
+                    uint16_t* x_hi, uint16_t* x_lo, float* x_rs, int lds, const float* w, const float* b,
                     int M, int C, float eps, int seg, int seg_stride, int seg_off, omt_stream_t stream);
 
 /* Tuning knobs (process-wide): "pdl" = 0 (default; measured 2-4 % slower when on) | 1 programmatic dependent launch;
  * "peg_kernel" = 3 (default) | 4 (cp.async gather + packed f32x2 FMAs; bit-identical);
  * "attn_kernel" = 3 (default: tcgen05 spatial attention core when N % 128 == 0) | 1 (CUDA-core fp32);
- * "f16_bn" = 256 (default: 256 x 256 tiles, one TMEM buffer released as soon as the epilogue has drained it into
- * registers) | 128 (256 x 128 tiles, double-buffered accumulators) for omt_linear_h. */
+ * "f16_bn" = 0 (default: by shape) | 256 (256 x 256 tiles, one TMEM buffer released as soon as the epilogue has drained
+ * it into registers) | 128 (256 x 128 tiles, double-buffered accumulators): tile width of omt_linear_h's two-accumulator form. */
 int omt_set_option(const char* name, int value);
 
 #ifdef __cplusplus

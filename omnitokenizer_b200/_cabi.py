@@ -21,7 +21,8 @@ ABI_VERSION = 2
 
 class LinearHArgs(ctypes.Structure):
     """omt_linear_h_args (include/omnitok_b200.h), field for field."""
-    _fields_ = [("a_hi", c_void_p), ("a_lo", c_void_p), ("a2_hi", c_void_p), ("a2_lo", c_void_p), ("n_split", c_int),
+    _fields_ = [("a_hi", c_void_p), ("a_lo", c_void_p), ("a_rs", c_void_p), ("a2_rs", c_void_p), ("w_scale", c_float),
+                ("a2_hi", c_void_p), ("a2_lo", c_void_p), ("n_split", c_int),
                 ("lda", c_int), ("a_seg", c_int), ("a_seg_stride", c_int), ("a_seg_off", c_int),
                 ("w_hi", c_void_p), ("w_lo", c_void_p),
                 ("c", c_void_p), ("ldc", c_int), ("c_seg", c_int), ("c_seg_stride", c_int), ("c_seg_off", c_int),
@@ -46,9 +47,9 @@ SIGNATURES = {
     "omt_linear_h": (c_int, [POINTER(LinearHArgs), c_void_p]),
     "omt_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int,
                               c_int, c_void_p]),
-    "omt_layernorm_h": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                                c_void_p, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
-    "omt_patchify_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_float, c_void_p]),
+    "omt_layernorm_h": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
+    "omt_patchify_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_float, c_void_p]),
     "omt_unpatchify": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "omt_unpatchify_u8": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_float] * 5 + [c_void_p]),
     "omt_peg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -135,7 +136,7 @@ def linear_h(**kw):
 
 
 # process-wide kernel selectors and their library defaults (omt_set_option); tests restore these after flipping them
-DEFAULT_OPTIONS = {"attn_kernel": 3, "peg_kernel": 3, "f16_bn": 256}
+DEFAULT_OPTIONS = {"attn_kernel": 3, "peg_kernel": 3, "f16_bn": 0}
 
 
 def set_option(name: str, value: int):

@@ -23,8 +23,13 @@
 //              then does the bias / residual / GELU / rope work and the stores -- fp32 outputs are staged as SWIZZLE_128B
 //              32 x 32 boxes in a warp-private slab and leave by TMA STORE; GEGLU writes the planes of U directly.
 // TMEM budget (512 columns, two accumulators per tile): BN = 256 -> one buffer (the early release keeps the tensor pipe
-// idle only for the drain); BN = 128 -> two buffers (epilogue fully overlapped, but twice the A traffic from L2 and
-// N = 128 MMAs).  omt_set_option("f16_bn", 128 | 256) selects; profiles/ has the A/B.
+// idle only for the drain, 128 lanes x 512 columns at the TMEM read rate); BN = 128 -> two buffers (epilogue fully
+// overlapped, but twice the A traffic from L2).  omt_set_option("f16_bn", 128 | 256) selects; profiles/ has the A/B.
+//
+// NACC = 1, the ROW-SCALED form (omt_common.cuh): when the A planes come from a producer that saw whole rows (LayerNorm,
+// patch gather) they carry a per-row power-of-two scale and an UNSCALED lo plane, the weights a per-matrix one; all three
+// products then share ONE accumulator -> 256-wide tiles AND double buffering, half the drain.  The epilogue multiplies by
+// the exact inverse scales (a_rs[row] * w_scale).
 #include "omt_common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
@@ -40,18 +45,20 @@ constexpr int EPI_WARPS = 8;
 constexpr int SLAB_BYTES = 4096;              // one 32 x 32 fp32 box per epilogue warp
 constexpr int THREADS = 64 + EPI_WARPS * 32;  // TMA, MMA, 8 epilogue warps
 
-template <int BN> struct Cfg {
+template <int BN, int NACC> struct Cfg {
   static constexpr int W_BYTES = (BN / 2) * BK * 2;                 // per plane, per CTA
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;     // A_hi, A_lo, W_hi, W_lo
   static constexpr int STAGES = (BN == 256) ? 3 : 4;                // 192 KiB either way
-  static constexpr int NBUF = 512 / (2 * BN);                       // TMEM accumulator buffers (main + cross per buffer)
+  static constexpr int NBUF = 512 / (NACC * BN) >= 2 ? 2 : 1;       // TMEM accumulator buffers (NACC accumulators each)
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * SLAB_BYTES + 1024;
 };
 
 struct HArgs {
   int M, N, K;
   int num_m_blk, num_n_blk, n_split;
-  int a_seg;                                  // A row map (segment length or 0); the strides live in the tensor maps
+  int a_seg, a_seg_stride, a_seg_off;         // A row map (the TMA strides live in the tensor maps; the epilogue needs it for a_rs)
+  const float* a_rs; const float* a2_rs;      // NACC == 1: inverse row scales of the A planes (second: dual-A columns >= n_split)
+  float w_scale;                              // NACC == 1: inverse scale of the W planes
   int c_seg, c_seg_stride, c_seg_off;         // C / residual row map
   const float* bias;
   const float* residual; int ldr;
@@ -79,15 +86,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, int EPI>
+template <int BN, int NACC, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
                 const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                 const __grid_constant__ CUtensorMap tmC, const HArgs g) {
-  using C_ = Cfg<BN>;
+  using C_ = Cfg<BN, NACC>;
   constexpr int W_BYTES = C_::W_BYTES, STAGE_BYTES = C_::STAGE_BYTES, STAGES = C_::STAGES, NBUF = C_::NBUF;
-  static_assert(NBUF == 1 || NBUF == 2, "TMEM: main + cross accumulators of BN columns, NBUF buffers");
+  static_assert(NBUF * NACC * BN <= 512, "TMEM: NACC accumulators of BN columns, NBUF buffers");
   constexpr uint32_t IDESC = idesc_f16(256, BN, false, false);          // fp16 x fp16 -> fp32, UMMA 256 x BN x 16
 
   extern __shared__ uint8_t smem_raw[];
@@ -177,8 +184,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         const uint32_t acc = tcount % NBUF, acc_ph = (tcount / NBUF) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
-        const uint32_t d_main = tmem_base + acc * (2 * BN);
-        const uint32_t d_cross = d_main + BN;
+        const uint32_t d_main = tmem_base + acc * (NACC * BN);
+        const uint32_t d_cross = d_main + (NACC - 1) * BN;              // == d_main in the row-scaled (single accumulator) form
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -193,7 +200,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
               const uint64_t adv = (uint64_t)(k * 32 >> 4);             // 16 elements = 32 bytes inside the swizzle row
               mma_f16_pair(d_cross, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
               mma_f16_pair(d_cross, d_ahi + adv, d_wlo + adv, IDESC, 1);
-              mma_f16_pair(d_main, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
+              mma_f16_pair(d_main, d_ahi + adv, d_whi + adv, IDESC, NACC == 1 ? 1u : (uint32_t)((kb | k) != 0));
             }
             tc_commit_pair(&empty[s]);
             if (kb == num_kb - 1) tc_commit_pair(&tmem_full[acc]);
@@ -223,7 +230,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       // TMA store coordinates of the warp's 32 rows (a row-map segment is a multiple of 32 rows)
       int cm1 = mw, cm2 = 0;
       if (g.c_seg > 0) { cm1 = mw % g.c_seg; cm2 = mw / g.c_seg; }
-      const uint32_t t_main = tmem_base + lane_addr + acc * (2 * BN) + (uint32_t)(hf * (BN / 2));
+      const uint32_t t_main = tmem_base + lane_addr + acc * (NACC * BN) + (uint32_t)(hf * (BN / 2));
+      float out_scale = 1.0f;                                          // row-scaled form: exact inverse of the operand scales
+      if (NACC == 1) {
+        const float* rs = (n_blk * BN >= g.n_split) ? g.a2_rs : g.a_rs;
+        out_scale = g.w_scale * (row_ok ? __ldg(rs + map_row(m, g.a_seg, g.a_seg_stride, g.a_seg_off)) : 1.0f);
+      }
 
       // residual row segments (8 x 16 bytes per lane and chunk) ride in ONE register buffer: the next chunk's loads are
       // issued right after the current chunk's adds, so their latency hides behind the box store
@@ -237,7 +249,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           if (rrow != nullptr && row_ok && n < g.N) res[i] = *reinterpret_cast<const float4*>(rrow + n + 4 * i);
         }
       };
-      if (EPI == OMT_EPI_NONE && NBUF == 2) load_res(0);      // two buffers = 64 accumulator registers: room to prefetch
+      if (EPI == OMT_EPI_NONE && BN == 128) load_res(0);      // 64 accumulator registers: room to prefetch
 
       // ---- drain: this lane's row of both accumulators -> registers (main + cross * 2^-11), then release the buffer
       float v[CH][32];
@@ -245,11 +257,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        float x[32];
-        tmem_ld32(t_main + (uint32_t)(BN + c * 32), x);
-        tmem_ld32(t_main + (uint32_t)(c * 32), v[c]);
+        if (NACC == 2) {
+          float x[32];
+          tmem_ld32(t_main + (uint32_t)(BN + c * 32), x);
+          tmem_ld32(t_main + (uint32_t)(c * 32), v[c]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[c][j] = fmaf(x[j], 1.0f / F16X3_LO_SCALE, v[c][j]);
+          for (int j = 0; j < 32; ++j) v[c][j] = fmaf(x[j], 1.0f / F16X3_LO_SCALE, v[c][j]);
+        } else {
+          tmem_ld32(t_main + (uint32_t)(c * 32), v[c]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[c][j] *= out_scale;
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -357,7 +375,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         }
       } else {
         // ---- plain: (+bias)(+residual), fp32 box by TMA store
-        if (NBUF == 1) load_res(0);
+        if (BN != 128) load_res(0);
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const int n = n0 + c * 32;
@@ -430,14 +448,14 @@ static int row_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void
   return encode_map(m, dt, base, 3, dims, strides, box);
 }
 
-template <int BN, int EPI>
+template <int BN, int NACC, int EPI>
 static int launch(const CUtensorMap* maps, const HArgs& g, cudaStream_t st) {
-  auto kern = gemm_f16_kernel<BN, EPI>;
+  auto kern = gemm_f16_kernel<BN, NACC, EPI>;
   static bool attr[64];
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr[dev]) {
-    OMT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    OMT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, NACC>::SMEM));
     attr[dev] = true;
   }
   const int num_tiles = g.num_m_blk * g.num_n_blk;
@@ -446,7 +464,7 @@ static int launch(const CUtensorMap* maps, const HArgs& g, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = Cfg<BN>::SMEM;
+  cfg.dynamicSmemBytes = Cfg<BN, NACC>::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -460,12 +478,15 @@ static int launch(const CUtensorMap* maps, const HArgs& g, cudaStream_t st) {
 
 }  // namespace f16g
 
-int g_f16_bn = 256;   // omt_set_option("f16_bn", 128|256): tile N (256: one TMEM buffer, early release; 128: two buffers)
+int g_f16_bn = 0;   // omt_set_option("f16_bn", 0|128|256): tile N of the two-accumulator form (0 = by shape)
 
 // A planes: [M, lda] fp16; W planes: [n_pad, K] fp16 (rows padded to 256); C fp32 (plain / QKV) or U planes (GEGLU)
 int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   using namespace f16g;
-  const int BN = g_f16_bn;
+  const bool rs = a.a_rs != nullptr;                  // row-scaled planes: one accumulator, 256-wide double-buffered tiles
+  // two accumulators: 256-wide tiles hold ONE TMEM buffer (the drain is exposed: 1/3 of a K = 512 main loop), 128-wide
+  // tiles two (but read A from L2 once per 128 columns) -- measured on B200: 128 wins only for the K = N = 512 shapes
+  int BN = rs ? 256 : (g_f16_bn != 0 ? g_f16_bn : ((a.K <= 512 && a.N <= 512) ? 128 : 256));
   OMT_REQUIRE(a.K % BK == 0 && a.lda % 8 == 0, "omt_linear_h: K=%d must be a multiple of 64 and lda %% 8 == 0", a.K);
   if (a.a_seg > 0)
     OMT_REQUIRE(a.a_seg % 64 == 0 && a.M % a.a_seg == 0, "omt_linear_h: A row-map segment %d must be a multiple of 64 dividing M=%d", a.a_seg, a.M);
@@ -499,13 +520,14 @@ int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   g.num_m_blk = (a.M + 2 * BM - 1) / (2 * BM);
   g.num_n_blk = (a.N + BN - 1) / BN;
   g.n_split = dual ? a.n_split : 0x7fffffff;
-  g.a_seg = a.a_seg;
+  g.a_seg = a.a_seg; g.a_seg_stride = a.a_seg_stride; g.a_seg_off = a.a_seg_off;
+  g.a_rs = a.a_rs; g.a2_rs = dual ? a.a2_rs : a.a_rs; g.w_scale = a.w_scale;
   g.c_seg = a.c_seg; g.c_seg_stride = a.c_seg_stride; g.c_seg_off = a.c_seg_off;
   g.bias = a.bias; g.residual = a.residual; g.ldr = a.ldr;
   g.u_hi = a.u_hi; g.u_lo = a.u_lo; g.ldu = a.ldu;
   g.rope_cos = a.rope_cos; g.rope_sin = a.rope_sin; g.q_scale = a.q_scale; g.k_scale = a.k_scale;
   g.qk_cols = a.qk_cols; g.tokens = a.tokens > 0 ? a.tokens : 1;
-#define OMT_F16_LAUNCH(EPI_) (BN == 256 ? launch<256, EPI_>(maps, g, st) : launch<128, EPI_>(maps, g, st))
+#define OMT_F16_LAUNCH(EPI_) (rs ? launch<256, 1, EPI_>(maps, g, st) : (BN == 256 ? launch<256, 2, EPI_>(maps, g, st) : launch<128, 2, EPI_>(maps, g, st)))
   if (a.epilogue == OMT_EPI_QKV) return OMT_F16_LAUNCH(OMT_EPI_QKV);
   if (a.epilogue == OMT_EPI_GEGLU) return OMT_F16_LAUNCH(OMT_EPI_GEGLU);
   return OMT_F16_LAUNCH(OMT_EPI_NONE);
@@ -521,6 +543,8 @@ extern "C" int omt_linear_h(const omt_linear_h_args* a, omt_stream_t stream) {
   OMT_REQUIRE(a != nullptr, "omt_linear_h: null argument block");
   OMT_REQUIRE(a->a_hi && a->a_lo && a->w_hi && a->w_lo, "omt_linear_h: null operand plane");
   OMT_REQUIRE((a->a2_hi == nullptr) == (a->a2_lo == nullptr), "omt_linear_h: the second A needs both planes");
+  OMT_REQUIRE(a->a2_hi == nullptr || ((a->a_rs == nullptr) == (a->a2_rs == nullptr)), "omt_linear_h: both A operands must use the same plane format");
+  OMT_REQUIRE(a->a_rs == nullptr || (a->w_scale > 0.f && a->w_scale < 3.0e38f), "omt_linear_h: row-scaled planes need the weight scale");
   OMT_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "omt_linear_h: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   OMT_REQUIRE(a->epilogue == OMT_EPI_NONE || a->epilogue == OMT_EPI_GEGLU || a->epilogue == OMT_EPI_QKV, "omt_linear_h: unknown epilogue %d", a->epilogue);
   if (a->epilogue == OMT_EPI_GEGLU) {

@@ -110,6 +110,33 @@ __device__ __forceinline__ void store_split2(uint16_t* hi, uint16_t* lo, size_t 
   *reinterpret_cast<uint32_t*>(lo + off) = l;
 }
 
+// ---- row-scaled planes (single-accumulator form) ------------------------------------------------------------------------
+// When a producer sees a whole row (LayerNorm, the patch gather) it can do better than the fixed 2^11: the row is
+// multiplied by a power of two that puts its largest magnitude in [2^14, 2^15), hi = fp16(x'), lo = fp16(x' - hi)
+// UNSCALED.  fp16 keeps 11 significant bits down to 2^-14, so every element within 2^16 of the row maximum is carried to
+// 2^-23 relative and smaller ones to 2^-40 of the row maximum.  With the weights pre-scaled the same way per matrix, the
+// three products hi.hi + hi.lo + lo.hi share ONE fp32 accumulator (half the TMEM, half the drain) and the epilogue
+// multiplies by the exact inverse scales.  row_scale(): scale and inverse for a row whose largest |value| is mx.
+__device__ __forceinline__ void row_scale(float mx, float& scale, float& inv) {
+  uint32_t eb = (__float_as_uint(mx) >> 23) & 0xffu;          // mx in [2^(eb-127), 2^(eb-126))
+  eb = eb < 15u ? 15u : (eb > 254u ? 254u : eb);              // all-zero rows / inf: clamp, both factors stay normal floats
+  scale = __uint_as_float((268u - eb) << 23);                 // 2^(141 - eb): row maximum -> [2^14, 2^15)
+  inv = __uint_as_float((eb - 14u) << 23);                    // 2^(eb - 141)
+}
+__device__ __forceinline__ void split2u(float a, float b, uint32_t& hi2, uint32_t& lo2) {     // a, b already row-scaled
+  hi2 = pack_f16x2_sat(a, b);
+  const float2 h = unpack_f16x2(hi2);
+  lo2 = pack_f16x2_sat(a - h.x, b - h.y);
+}
+__device__ __forceinline__ void store_split4u(uint16_t* hi, uint16_t* lo, size_t off, float4 v, float scale) {
+  uint2 h, l;
+  split2u(v.x * scale, v.y * scale, h.x, l.x);
+  split2u(v.z * scale, v.w * scale, h.y, l.y);
+  *reinterpret_cast<uint2*>(hi + off) = h;
+  *reinterpret_cast<uint2*>(lo + off) = l;
+}
+__device__ __forceinline__ float max4abs(float4 v) { return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))); }
+
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

@@ -46,10 +46,11 @@ int sm_count() {
 // ------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, whole row in registers (C <= 1024), two-pass statistics.
 // ------------------------------------------------------------------------------------------
-struct LnPlanes {          // optional fp16 hi / bf16 lo operand planes (omt_layernorm_h), written at the LOGICAL row
+struct LnPlanes {          // optional fp16 hi / lo operand planes (omt_layernorm_h), written at the LOGICAL row
   uint16_t* y_hi; uint16_t* y_lo;    // normalised row
   uint16_t* x_hi; uint16_t* x_lo;    // raw input row (Attention.forward projects k, v from it)
   int lds;
+  float* y_rs; float* x_rs;          // non-NULL: row-scaled planes (omt_common.cuh), the inverse row scale goes here
 };
 
 template <int NV>   // float4 chunks per lane
@@ -73,10 +74,23 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (c < C) {
       v[i] = *reinterpret_cast<const float4*>(xr + c);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-      if (pl.x_hi != nullptr) store_split4(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i]);
+      if (pl.x_hi != nullptr && pl.x_rs == nullptr) store_split4(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i]);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+  if (pl.x_hi != nullptr && pl.x_rs != nullptr) {      // row-scaled planes of the raw row
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) mx = fmaxf(mx, max4abs(v[i]));
+    float sc, inv;
+    row_scale(warp_max(mx), sc, inv);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) store_split4u(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i], sc);
+    }
+    if (lane == 0) pl.x_rs[lrow] = inv;
   }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
@@ -90,6 +104,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
   float* yr = y + (size_t)row * ldy;
+  float omx = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
@@ -103,8 +118,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
       }
       if (y != nullptr) *reinterpret_cast<float4*>(yr + c) = o;
-      if (pl.y_hi != nullptr) store_split4(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, o);
+      if (pl.y_hi != nullptr && pl.y_rs == nullptr) store_split4(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, o);
+      v[i] = o;                                        // kept for the row-scaled form below
+      omx = fmaxf(omx, max4abs(o));
     }
+  }
+  if (pl.y_hi != nullptr && pl.y_rs != nullptr) {      // row-scaled planes of the normalised row
+    float sc, inv;
+    row_scale(warp_max(omx), sc, inv);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) store_split4u(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, v[i], sc);
+    }
+    if (lane == 0) pl.y_rs[lrow] = inv;
   }
 }
 
@@ -115,7 +142,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <int NV>
 __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restrict__ video,
                                                           float* __restrict__ A, uint16_t* __restrict__ A_hi,
-                                                          uint16_t* __restrict__ A_lo,
+                                                          uint16_t* __restrict__ A_lo, float* __restrict__ A_rs,
                                                           const float* __restrict__ lw,
                                                           const float* __restrict__ lb, int rows,
                                                           int Cin, int T, int H, int W, int p, int pt,
@@ -152,15 +179,28 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
     }
   }
   const size_t rbase = (size_t)row * K;
-  if (lw == nullptr) {        // plain im2col (patch_embed='cnn': the strided Conv3d is a GEMM on raw patch vectors)
+  // write a finished row: fp32, 2^11-scaled planes, or row-scaled planes (+ the inverse row scale)
+  auto emit = [&](float4 (&o)[NV]) {
+    float sc = 1.f, inv = 1.f;
+    if (A_rs != nullptr) {
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) mx = fmaxf(mx, max4abs(o[i]));
+      row_scale(warp_max(mx), sc, inv);
+      if (lane == 0) A_rs[row] = inv;
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int f = (i * 32 + lane) * 4;
       if (f < K) {
-        if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, v[i]);
-        else *reinterpret_cast<float4*>(A + rbase + f) = v[i];
+        if (A_rs != nullptr) store_split4u(A_hi, A_lo, rbase + f, o[i], sc);
+        else if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, o[i]);
+        else *reinterpret_cast<float4*>(A + rbase + f) = o[i];
       }
     }
+  };
+  if (lw == nullptr) {        // plain im2col (patch_embed='cnn': the strided Conv3d is a GEMM on raw patch vectors)
+    emit(v);
     return;
   }
   const float mean = warp_sum(s) / (float)K;
@@ -183,10 +223,10 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
       float4 o;
       o.x = v[i].x * rstd * g.x + bb.x; o.y = v[i].y * rstd * g.y + bb.y;
       o.z = v[i].z * rstd * g.z + bb.z; o.w = v[i].w * rstd * g.w + bb.w;
-      if (A_hi != nullptr) store_split4(A_hi, A_lo, rbase + f, o);
-      else *reinterpret_cast<float4*>(A + rbase + f) = o;
+      v[i] = o;
     }
   }
+  emit(v);
 }
 
 __global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict__ P,
@@ -641,24 +681,26 @@ extern "C" int omt_layernorm(const float* x, int ldx, float* y, int ldy, const f
                              int M, int C, float eps, int seg, int seg_stride, int seg_off,
                              omt_stream_t stream) {
   OMT_REQUIRE(y != nullptr, "omt_layernorm: null pointer");
-  omt::LnPlanes pl{nullptr, nullptr, nullptr, nullptr, 0};
+  omt::LnPlanes pl{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   return layernorm_impl("omt_layernorm", x, ldx, y, ldy, pl, w, b, M, C, eps, seg, seg_stride, seg_off, stream);
 }
 
-extern "C" int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, uint16_t* y_lo,
-                               uint16_t* x_hi, uint16_t* x_lo, int lds, const float* w, const float* b,
+extern "C" int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, uint16_t* y_lo, float* y_rs,
+                               uint16_t* x_hi, uint16_t* x_lo, float* x_rs, int lds, const float* w, const float* b,
                                int M, int C, float eps, int seg, int seg_stride, int seg_off, omt_stream_t stream) {
-  omt::LnPlanes pl{y_hi, y_lo, x_hi, x_lo, lds};
+  OMT_REQUIRE((y_rs == nullptr || y_hi != nullptr) && (x_rs == nullptr || x_hi != nullptr), "omt_layernorm_h: row scales without planes");
+  omt::LnPlanes pl{y_hi, y_lo, x_hi, x_lo, lds, y_rs, x_rs};
   return layernorm_impl("omt_layernorm_h", x, ldx, y, ldy, pl, w, b, M, C, eps, seg, seg_stride, seg_off, stream);
 }
 
-extern "C" int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uint16_t* A_lo, const float* ln_w,
+extern "C" int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uint16_t* A_lo, float* A_rs, const float* ln_w,
                                const float* ln_b, int B, int Cin, int T, int H, int W, int p, int pt, int first,
                                float eps, omt_stream_t stream) {
   OMT_ENTER();
   OMT_REQUIRE(video && (A || A_hi) && ((ln_w == nullptr) == (ln_b == nullptr)) && ((A_hi == nullptr) == (A_lo == nullptr)),
               "omt_patchify_ln: null pointer");
   OMT_REQUIRE(((uintptr_t)A_hi | (uintptr_t)A_lo) % 8 == 0, "omt_patchify_ln: planes must be 8-byte aligned");
+  OMT_REQUIRE(A_rs == nullptr || A_hi != nullptr, "omt_patchify_ln: row scales without planes");
   OMT_REQUIRE(p % 4 == 0 && H % p == 0 && W % p == 0, "omt_patchify_ln: patch %d must be a multiple of 4 dividing %dx%d", p, H, W);
   OMT_REQUIRE(first || (T > 1 && (T - 1) % pt == 0), "omt_patchify_ln: (T-1) %% pt != 0");
   const int PT = first ? 1 : pt;
@@ -670,11 +712,11 @@ extern "C" int omt_patchify_ln(const float* video, float* A, uint16_t* A_hi, uin
   dim3 grid((unsigned)((rows + 7) / 8)), block(256);
   const int nv = (K / 4 + 31) / 32;
   if (nv <= 2)
-    OMT_CUDA(launch_k(patchify_ln_kernel<2>, grid, block, 0, st, video, A, A_hi, A_lo, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<2>, grid, block, 0, st, video, A, A_hi, A_lo, A_rs, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   else if (nv <= 6)
-    OMT_CUDA(launch_k(patchify_ln_kernel<6>, grid, block, 0, st, video, A, A_hi, A_lo, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<6>, grid, block, 0, st, video, A, A_hi, A_lo, A_rs, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   else
-    OMT_CUDA(launch_k(patchify_ln_kernel<8>, grid, block, 0, st, video, A, A_hi, A_lo, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
+    OMT_CUDA(launch_k(patchify_ln_kernel<8>, grid, block, 0, st, video, A, A_hi, A_lo, A_rs, ln_w, ln_b, (int)rows, Cin, T, H, W, p, pt, first, eps));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
@@ -804,7 +846,7 @@ extern "C" int omt_set_option(const char* name, int value) {
     return OMT_OK;
   }
   if (strcmp(name, "f16_bn") == 0) {
-    if (value != 128 && value != 256) { omt::set_error("f16_bn must be 128 or 256"); return OMT_E_ARG; }
+    if (value != 0 && value != 128 && value != 256) { omt::set_error("f16_bn must be 0, 128 or 256"); return OMT_E_ARG; }
     omt::g_f16_bn = value;
     return OMT_OK;
   }

@@ -31,16 +31,18 @@ def default_math() -> str:
 class Planes:
     """fp16 hi / lo operand planes of an [M, ld] fp32 matrix (the A operands of the f16x3 GEMMs; layout.split_f16)."""
 
-    def __init__(self, device, M: int, ld: int):
+    def __init__(self, device, M: int, ld: int, row_scaled: bool = False):
         self.buf = torch.empty(2, M, ld, device=device, dtype=torch.int16)
         self.hi, self.lo, self.ld = self.buf[0], self.buf[1], ld
+        # row-scaled form (written by producers that see whole rows): inverse per-row scales; None = the 2^11-scaled lo form
+        self.rs = torch.empty(M, device=device, dtype=torch.float32) if row_scaled else None
 
 
 class PackedLinear:
     """nn.Linear weight in GEMM layout: rows padded to 128, K padded, optional tf32 hi/lo split."""
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], device, math: int,
-                 k_pad: Optional[int] = None, geglu: Optional[Tuple[int, int]] = None):
+                 k_pad: Optional[int] = None, geglu: Optional[Tuple[int, int]] = None, row_scaled: bool = False):
         w = weight.detach().to(device=device, dtype=torch.float32)
         if geglu is not None:
             inner, ku = geglu
@@ -53,12 +55,15 @@ class PackedLinear:
         if math == _cabi.MATH_3XTF32:
             hi = L.tf32_round(w)
             self.w, self.w_lo = hi, (w - hi).contiguous()
+        elif math == _cabi.MATH_F16X3 and row_scaled:
+            self.w, self.w_lo, self.w_scale = L.split_f16_rs(w)      # fp16 planes, one scale per matrix (single-accumulator GEMM)
         elif math == _cabi.MATH_F16X3:
-            self.w, self.w_lo = L.split_f16(w)          # fp16 operand planes
+            self.w, self.w_lo = L.split_f16(w)          # fp16 operand planes, lo scaled by 2^11 (two-accumulator GEMM)
         else:
             self.w, self.w_lo = w, None
         self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
         self.math = math
+        self.row_scaled = row_scaled and math == _cabi.MATH_F16X3
 
 
 class Workspace:
@@ -71,8 +76,9 @@ class Workspace:
         self.QKV = torch.empty(M, 3 * C, **f)
         self.P = torch.empty(M, kmax, **f)       # patch matrix (pixels side), rows x K
         if planes:     # f16x3: every GEMM A operand lives as fp16 hi / lo planes written by its producer
-            self.XNp, self.XSp, self.Op = Planes(device, M, C), Planes(device, M, C), Planes(device, M, C)
-            self.Up, self.Pp = Planes(device, M, ku), Planes(device, M, kmax)
+            self.XNp, self.XSp = Planes(device, M, C, True), Planes(device, M, C, True)     # LayerNorm sees whole rows
+            self.Op, self.Up = Planes(device, M, C), Planes(device, M, ku)                  # attention heads / GEGLU tiles do not
+            self.Pp = Planes(device, M, kmax, True)
         else:
             self.XN = torch.empty(M, C, **f)
             self.O = torch.empty(M, C, **f)
@@ -152,7 +158,7 @@ class Engine:
             d["norm_g"], d["norm_b"] = f32(sd[ap + ".norm.gamma"]), f32(sd[ap + ".norm.beta"])
             d["q_scale"], d["k_scale"] = f32(sd[ap + ".q_scale"]), f32(sd[ap + ".k_scale"])
             # [Wq; Wkv] stacked: one dual-A GEMM writes q | k | v into the QKV buffer
-            d["to_qkv"] = PL(torch.cat([sd[ap + ".to_q.weight"], sd[ap + ".to_kv.weight"]], dim=0), None)
+            d["to_qkv"] = PL(torch.cat([sd[ap + ".to_q.weight"], sd[ap + ".to_kv.weight"]], dim=0), None, row_scaled=True)
             d["to_out"] = lin(ap + ".to_out", bias=False)
             ff(d, lp + ".3")
             return d
@@ -163,14 +169,14 @@ class Engine:
             d["norm_g"], d["norm_b"] = f32(sd[ap + ".norm.gamma"]), f32(sd[ap + ".norm.beta"])
             d["bias"] = L.window_bias(sd[ap + ".relative_position_bias_table"].detach().float().cpu(),
                                       sd[ap + ".relative_position_index"].cpu(), self.ws).to(dev)
-            d["qkv"] = lin(ap + ".qkv", bias=False)
+            d["qkv"] = lin(ap + ".qkv", bias=False, row_scaled=True)
             d["proj"] = lin(ap + ".proj")
             ff(d, lp + ".3")
             return d
 
         def ff(d, fp):
             d["ff_g"], d["ff_b"] = f32(sd[fp + ".0.weight"]), f32(sd[fp + ".0.bias"])
-            d["ff1"] = PL(sd[fp + ".1.weight"], None, geglu=(self.inner, self.ku))
+            d["ff1"] = PL(sd[fp + ".1.weight"], None, geglu=(self.inner, self.ku), row_scaled=True)
             d["ff2"] = PL(sd[fp + ".4.weight"], None, k_pad=self.ku)
 
         def transformer(pre, block):
@@ -206,7 +212,7 @@ class Engine:
                 w = sd[pre + ".0.weight"].float().reshape(self.C, -1)                 # (dim, c*pt*p*p)
                 s_, t_ = bn_affine(pre + ".1")
                 self.pe[key] = dict(ln1_g=None, ln1_b=None, ln2_g=None, ln2_b=None,
-                                    lin=PL(w * s_[:, None], sd[pre + ".0.bias"].float() * s_ + t_))
+                                    lin=PL(w * s_[:, None], sd[pre + ".0.bias"].float() * s_ + t_, row_scaled=True))
             self.px = {}
             for key, pre in (("first", "decoder.to_pixels_first_frame"), ("rest", "decoder.to_pixels")):
                 wt = sd[pre + ".1.weight"].float()                                    # (dim, channels, pt, p, p)
@@ -214,12 +220,13 @@ class Engine:
                 s_, t_ = bn_affine(pre + ".2")
                 w = wt.reshape(self.C, -1).t() * s_.repeat_interleave(per_c)[:, None]  # (channels*pt*p*p, dim)
                 bias = (sd[pre + ".1.bias"].float() * s_ + t_).repeat_interleave(per_c)
-                self.px[key] = PL(w.contiguous(), bias)
+                self.px[key] = PL(w.contiguous(), bias, row_scaled=True)
         else:
             for key, pre in (("first", "encoder.to_patch_emb_first_frame"), ("rest", "encoder.to_patch_emb")):
-                self.pe[key] = dict(ln1_g=f32(sd[pre + ".1.weight"]), ln1_b=f32(sd[pre + ".1.bias"]), lin=lin(pre + ".2"),
+                self.pe[key] = dict(ln1_g=f32(sd[pre + ".1.weight"]), ln1_b=f32(sd[pre + ".1.bias"]), lin=lin(pre + ".2", row_scaled=True),
                                     ln2_g=f32(sd[pre + ".3.weight"]), ln2_b=f32(sd[pre + ".3.bias"]))
-            self.px = {"first": lin("decoder.to_pixels_first_frame.0"), "rest": lin("decoder.to_pixels.0")}
+            self.px = {"first": lin("decoder.to_pixels_first_frame.0", row_scaled=True),
+                       "rest": lin("decoder.to_pixels.0", row_scaled=True)}
         self.pre_w, self.pre_b = f32(sd["pre_vq_conv.1.weight"]), f32(sd["pre_vq_conv.1.bias"])
         self.post_w, self.post_b = f32(sd["post_vq_conv.1.weight"]), f32(sd["post_vq_conv.1.bias"])
         E = sd["codebook.embeddings"].detach().float()
@@ -265,11 +272,15 @@ class Engine:
     def _linear_h(self, A: Planes, lin: PackedLinear, M, *, C=None, ldc=0, U: Optional[Planes] = None, A2: Optional[Planes] = None,
                   n_split=0, a_map=(0, 0, 0), c_map=(0, 0, 0), residual=None, ldr=0, epi=_cabi.EPI_NONE, qk=None):
         """nn.Linear on operand planes (tcgen05 f16x3).  U: GEGLU output planes; qk: (q_scale, k_scale, cos, sin, qk_cols, tokens)."""
+        if (A.rs is not None) != lin.row_scaled:
+            raise RuntimeError("operand planes and weight planes are in different f16x3 forms (row-scaled vs 2^11-scaled lo)")
         kw = dict(a_hi=A.hi, a_lo=A.lo, lda=A.ld, a_seg=a_map[0], a_seg_stride=a_map[1], a_seg_off=a_map[2],
                   w_hi=lin.w, w_lo=lin.w_lo, c=C, ldc=ldc, c_seg=c_map[0], c_seg_stride=c_map[1], c_seg_off=c_map[2],
                   M=M, N=lin.n, K=lin.k, bias=lin.bias, residual=residual, ldr=ldr, epilogue=epi)
+        if A.rs is not None:
+            kw.update(a_rs=A.rs, w_scale=lin.w_scale)
         if A2 is not None:
-            kw.update(a2_hi=A2.hi, a2_lo=A2.lo, n_split=n_split)
+            kw.update(a2_hi=A2.hi, a2_lo=A2.lo, a2_rs=A2.rs, n_split=n_split)
         if U is not None:
             kw.update(u_hi=U.hi, u_lo=U.lo, ldu=U.ld)
         if qk is not None:
@@ -283,8 +294,8 @@ class Engine:
     def _ln_h(self, x, yp: Planes, g, b, M, xp: Optional[Planes] = None):
         """LayerNorm straight into the operand planes of the consuming GEMM (+ planes of the raw row for to_kv)."""
         C = self.C
-        _cabi.call("omt_layernorm_h", x, C, None, 0, yp.hi, yp.lo, None if xp is None else xp.hi,
-                   None if xp is None else xp.lo, yp.ld, g, b, M, C, 1e-5, 0, 0, 0)
+        _cabi.call("omt_layernorm_h", x, C, None, 0, yp.hi, yp.lo, yp.rs, None if xp is None else xp.hi,
+                   None if xp is None else xp.lo, None if xp is None else xp.rs, yp.ld, g, b, M, C, 1e-5, 0, 0, 0)
 
     # ------------------------------------------------------------------ transformer
     def _transformer(self, tr, ws: Workspace, B, T, h, w, temporal: bool, out_planes: Optional[Planes] = None):
@@ -405,12 +416,12 @@ class Engine:
         def embed(pe, first, rows, K, cmap):
             if self.planes:
                 Pp = Planes.__new__(Planes)          # dense [rows, K] view at the start of the patch planes
-                Pp.hi, Pp.lo, Pp.ld = ws.Pp.hi, ws.Pp.lo, K
-                _cabi.call("omt_patchify_ln", x, None, Pp.hi, Pp.lo, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p,
-                           self.pt, first, 1e-5)
+                Pp.hi, Pp.lo, Pp.ld, Pp.rs = ws.Pp.hi, ws.Pp.lo, K, ws.Pp.rs
+                _cabi.call("omt_patchify_ln", x, None, Pp.hi, Pp.lo, Pp.rs, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W,
+                           self.p, self.pt, first, 1e-5)
                 self._linear_h(Pp, pe["lin"], rows, C=ws.X, ldc=C, c_map=cmap)
             else:
-                _cabi.call("omt_patchify_ln", x, ws.P, None, None, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p,
+                _cabi.call("omt_patchify_ln", x, ws.P, None, None, None, pe["ln1_g"], pe["ln1_b"], B, self.cin, T, H, W, self.p,
                            self.pt, first, 1e-5)
                 self._linear(ws.P, K, pe["lin"], ws.X, C, rows, c_map=cmap)
             if not self.cnn:

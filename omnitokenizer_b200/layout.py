@@ -84,6 +84,32 @@ def split_f16(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return hi.contiguous(), lo.contiguous()
 
 
+def split_f16_rs(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, float]:
+    """Row-scaled form for a WEIGHT matrix (one scale for the whole matrix): w' = w * 2^e with max |w'| in [2^14, 2^15),
+    hi = fp16(w'), lo = fp16(w' - hi) unscaled.  Returns (hi, lo, 2^-e)."""
+    w = w.float()
+    mx = float(w.abs().max())
+    e = 14 - math.floor(math.log2(mx)) if mx > 0 else 0
+    e = max(-100, min(100, e))
+    ws = w * (2.0 ** e)
+    hi = ws.clamp(-65504.0, 65504.0).to(torch.float16)
+    lo = (ws - hi.float()).to(torch.float16)
+    return hi.contiguous(), lo.contiguous(), 2.0 ** -e
+
+
+def split_rows_rs(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Row-scaled form of an activation matrix, the host twin of csrc/omt_common.cuh row_scale(): per row the power of two
+    that puts the largest magnitude in [2^14, 2^15).  Returns (hi, lo, inverse row scales [rows])."""
+    x = x.float()
+    eb = ((x.abs().amax(dim=1).contiguous().view(torch.int32) >> 23) & 0xFF).clamp(15, 254)
+    scale = ((268 - eb) << 23).view(torch.float32)
+    inv = ((eb - 14) << 23).view(torch.float32)
+    xs = x * scale[:, None]
+    hi = xs.clamp(-65504.0, 65504.0).to(torch.float16)
+    lo = (xs - hi.float()).to(torch.float16)
+    return hi.contiguous(), lo.contiguous(), inv.contiguous()
+
+
 def join_f16(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
     """fp32 value a pair of operand planes stands for (int16 views are reinterpreted as fp16)."""
     return hi.view(torch.float16).float() + lo.view(torch.float16).float() / F16X3_LO_SCALE

@@ -24,8 +24,8 @@ def timeit(fn, reps=7):
 
 
 SHAPES = [("qkv", 1536, 512, "qkv"), ("out+res", 512, 512, "res"), ("ff1+geglu", 2730, 512, "geglu"), ("ff2+res", 512, 1365, "res")]
-for scheme in [int(v) for v in os.environ.get("F16_BN", "256,128").split(",")]:
-  _cabi.set_option("f16_bn", scheme)
+for scheme in [int(v) for v in os.environ.get("F16_BN", "256,128,1").split(",")]:       # 1 = row-scaled single-accumulator form
+  _cabi.set_option("f16_bn", scheme if scheme > 1 else 0)
   for M in Ms:
     for name, N, K, kind in SHAPES:
         g = torch.Generator(device=dev).manual_seed(1)
@@ -51,15 +51,19 @@ for scheme in [int(v) for v in os.environ.get("F16_BN", "256,128").split(",")]:
                 else:
                     fn = lambda: _cabi.call("omt_linear", A, Kp, 0, 0, 0, hi, lo, R, 512, 0, 0, 0, M, Np, Kp, None, R, 512, _cabi.EPI_NONE, _cabi.MATH_3XTF32)
             else:
-                ah, al = L.split_f16(A); wh, wl = L.split_f16(L.pad_rows(W, 256))
+                rsk = {}
+                if scheme == 1:
+                    ah, al, ars = L.split_rows_rs(A); wh, wl, wsc = L.split_f16_rs(L.pad_rows(W, 256)); rsk = dict(a_rs=ars, w_scale=wsc)
+                else:
+                    ah, al = L.split_f16(A); wh, wl = L.split_f16(L.pad_rows(W, 256))
                 if kind == "geglu":
                     U = torch.empty(2, M, Np // 2, dtype=torch.int16, device=dev)
-                    fn = lambda: _cabi.linear_h(a_hi=ah, a_lo=al, lda=Kp, w_hi=wh, w_lo=wl, u_hi=U[0], u_lo=U[1], ldu=Np // 2, M=M, N=Np, K=Kp, epilogue=_cabi.EPI_GEGLU)
+                    fn = lambda: _cabi.linear_h(a_hi=ah, a_lo=al, lda=Kp, w_hi=wh, w_lo=wl, u_hi=U[0], u_lo=U[1], ldu=Np // 2, M=M, N=Np, K=Kp, epilogue=_cabi.EPI_GEGLU, **rsk)
                 elif kind == "qkv":
                     C = torch.empty(M, Np, device=dev)
-                    fn = lambda: _cabi.linear_h(a_hi=ah, a_lo=al, lda=Kp, w_hi=wh, w_lo=wl, c=C, ldc=Np, M=M, N=Np, K=Kp, epilogue=_cabi.EPI_NONE)
+                    fn = lambda: _cabi.linear_h(a_hi=ah, a_lo=al, lda=Kp, w_hi=wh, w_lo=wl, c=C, ldc=Np, M=M, N=Np, K=Kp, epilogue=_cabi.EPI_NONE, **rsk)
                 else:
-                    fn = lambda: _cabi.linear_h(a_hi=ah, a_lo=al, lda=Kp, w_hi=wh, w_lo=wl, c=R, ldc=512, M=M, N=Np, K=Kp, residual=R, ldr=512, epilogue=_cabi.EPI_NONE)
+                    fn = lambda: _cabi.linear_h(a_hi=ah, a_lo=al, lda=Kp, w_hi=wh, w_lo=wl, c=R, ldc=512, M=M, N=Np, K=Kp, residual=R, ldr=512, epilogue=_cabi.EPI_NONE, **rsk)
             try:
                 us = timeit(fn)
                 tf = flops / us / 1e6

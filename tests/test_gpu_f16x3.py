@@ -174,6 +174,7 @@ def test_plane_producers(cuda):
     """LayerNorm (+ raw-row planes), patch gather and the attention cores write planes that stand for the same fp32 values
     their fp32 forms produce (within the split's 2^-22 relative representation error)."""
     cabi = _cabi(bn)
+    from omnitokenizer_b200 import layout as L
     M = 320
     x = _rand((M, 512), 10, 3.0)
     g, b = _rand((512,), 11) + 1.0, _rand((512,), 12)
@@ -182,27 +183,44 @@ def test_plane_producers(cuda):
     yp = torch.zeros(2, M, 512, dtype=torch.int16, device=cuda)
     xp = torch.zeros(2, M, 512, dtype=torch.int16, device=cuda)
     y2 = torch.empty(M, 512, device=cuda)
-    cabi.call("omt_layernorm_h", x.to(cuda), 512, y2, 512, yp[0], yp[1], xp[0], xp[1], 512, g.to(cuda), b.to(cuda), M, 512,
-              1e-5, 0, 0, 0)
+    cabi.call("omt_layernorm_h", x.to(cuda), 512, y2, 512, yp[0], yp[1], None, xp[0], xp[1], None, 512, g.to(cuda), b.to(cuda),
+              M, 512, 1e-5, 0, 0, 0)
     d = (y - y2).abs()
     assert torch.equal(y, y2), f"fp32 output differs between the two entry points: max {d.max().item():.3e}, {int((d > 0).sum())} elements"
     tol = lambda t: 2.0 ** -21 * t.abs().max().item()
     assert (_join(yp[0], yp[1], bn) - y.cpu()).abs().max().item() <= tol(y.cpu())
     assert (_join(xp[0], xp[1], bn) - x).abs().max().item() <= tol(x)
-    cabi.call("omt_layernorm_h", x.to(cuda), 512, None, 0, yp[0], yp[1], None, None, 512, g.to(cuda), b.to(cuda), M, 512,
-              1e-5, 0, 0, 0)                                     # planes only
+    cabi.call("omt_layernorm_h", x.to(cuda), 512, None, 0, yp[0], yp[1], None, None, None, None, 512, g.to(cuda), b.to(cuda),
+              M, 512, 1e-5, 0, 0, 0)                             # planes only
     assert (_join(yp[0], yp[1], bn) - y.cpu()).abs().max().item() <= tol(y.cpu())
+    # row-scaled form: hi + lo (unscaled) times the inverse row scale; the scale puts the row maximum in [2^14, 2^15)
+    yrs, xrs = torch.zeros(M, device=cuda), torch.zeros(M, device=cuda)
+    cabi.call("omt_layernorm_h", x.to(cuda), 512, None, 0, yp[0], yp[1], yrs, xp[0], xp[1], xrs, 512, g.to(cuda), b.to(cuda),
+              M, 512, 1e-5, 0, 0, 0)
+    for pl, rs, want in ((yp, yrs, y.cpu()), (xp, xrs, x)):
+        hi, lo = pl[0].cpu().view(torch.float16).float(), pl[1].cpu().view(torch.float16).float()
+        got = (hi + lo) * rs.cpu()[:, None]
+        assert ((got - want).abs() <= 2.0 ** -22 * want.abs().amax(dim=1, keepdim=True)).all()
+        top = hi.abs().amax(dim=1)
+        assert (top >= 2.0 ** 14).all() and (top <= 2.0 ** 15).all()
+        h2, l2, inv2 = L.split_rows_rs(want)                      # the host twin agrees bit for bit
+        assert torch.equal(inv2, rs.cpu()) and torch.equal(h2.float(), hi) and torch.equal(l2.float(), lo)
     # patch gather
     shape = (2, 3, 5, 64, 64)
     v = _rand(shape, 13, 0.5)
     for is_first, K, rows in ((1, 192, 2 * 64), (0, 768, 2 * 64)):
         lw, lb = _rand((K,), 14) + 1.0, _rand((K,), 15)
         A = torch.empty(rows, K, device=cuda)
-        cabi.call("omt_patchify_ln", v.to(cuda), A, None, None, lw.to(cuda), lb.to(cuda), 2, 3, 5, 64, 64, 8, 4, is_first, 1e-5)
+        cabi.call("omt_patchify_ln", v.to(cuda), A, None, None, None, lw.to(cuda), lb.to(cuda), 2, 3, 5, 64, 64, 8, 4, is_first, 1e-5)
         Ap = torch.zeros(2, rows, K, dtype=torch.int16, device=cuda)
-        cabi.call("omt_patchify_ln", v.to(cuda), None, Ap[0], Ap[1], lw.to(cuda), lb.to(cuda), 2, 3, 5, 64, 64, 8, 4, is_first,
-                  1e-5)
+        cabi.call("omt_patchify_ln", v.to(cuda), None, Ap[0], Ap[1], None, lw.to(cuda), lb.to(cuda), 2, 3, 5, 64, 64, 8, 4,
+                  is_first, 1e-5)
         assert (_join(Ap[0], Ap[1], bn) - A.cpu()).abs().max().item() <= tol(A.cpu())
+        ars = torch.zeros(rows, device=cuda)
+        cabi.call("omt_patchify_ln", v.to(cuda), None, Ap[0], Ap[1], ars, lw.to(cuda), lb.to(cuda), 2, 3, 5, 64, 64, 8, 4,
+                  is_first, 1e-5)
+        got = (Ap[0].cpu().view(torch.float16).float() + Ap[1].cpu().view(torch.float16).float()) * ars.cpu()[:, None]
+        assert ((got - A.cpu()).abs() <= 2.0 ** -22 * A.cpu().abs().amax(dim=1, keepdim=True)).all()
     # attention cores
     nseq, N = 2, 256
     Ma = nseq * N
@@ -224,3 +242,72 @@ def test_plane_producers(cuda):
     cabi.call("omt_attn_temporal", p, 1536, p + 2048, 1536, p + 4096, 1536, o, None, None, 512, 2, 4, 64, 8, 8.0, 1)
     cabi.call("omt_attn_temporal", p, 1536, p + 2048, 1536, p + 4096, 1536, None, op[0], op[1], 512, 2, 4, 64, 8, 8.0, 1)
     assert (_join(op[0], op[1], bn) - o.cpu()).abs().max().item() <= tol(o.cpu())
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 512, 512), (320, 192, 512), (1024, 1024, 768), (4160, 2816, 512), (192, 512, 192)])
+def test_linear_h_row_scaled(cuda, M, N, K):
+    """Single-accumulator form: row-scaled A planes (per-row power-of-two scale, unscaled lo) x per-matrix-scaled W planes,
+    rows of very different magnitude in one call (1e-3 .. 1e3)."""
+    cabi = _cabi(0)
+    from omnitokenizer_b200 import layout as L
+    A, Wt, b, R = _rand((M, K), 1), _rand((N, K), 2, 0.05), _rand((N,), 3), _rand((M, N), 4)
+    A = A * torch.logspace(-3, 3, M)[:, None]
+    ref = (A.double() @ Wt.double().t() + b.double() + R.double()).float()
+    ah, al, ars = [t.to(cuda) for t in L.split_rows_rs(A)]
+    wh, wl, wsc = L.split_f16_rs(L.pad_rows(Wt, 256))
+    out = torch.full((M, N), float("nan"), device=cuda)
+    cabi.linear_h(a_hi=ah, a_lo=al, a_rs=ars, w_scale=wsc, lda=K, w_hi=wh.to(cuda), w_lo=wl.to(cuda), c=out, ldc=N, M=M, N=N, K=K,
+                  bias=b.to(cuda), residual=R.to(cuda), ldr=N, epilogue=cabi.EPI_NONE)
+    torch.cuda.synchronize()
+    scale = A.abs().amax(dim=1, keepdim=True).clamp_min(1.0)              # error bar relative to each row's magnitude
+    err = ((out.cpu() - ref).abs() / scale).max().item()
+    assert err < 2e-5, f"row-scaled f16x3 M{M} N{N} K{K}: max scaled err {err:.3e}"
+
+
+def test_linear_h_row_scaled_epilogues(cuda):
+    """Row-scaled form through the GEGLU and the dual-A QKV epilogues and the A row map (to_pixels reads X through one)."""
+    cabi = _cabi(0)
+    from omnitokenizer_b200 import layout as L
+    M, K, inner = 320, 512, 1365
+    ku = L.round_up(inner, 64)
+    A, W1 = _rand((M, K), 5, 2.0), _rand((2 * inner, K), 6, 0.05)
+    y = A.double() @ W1.double().t()
+    ref = (oo.gelu_erf(y[:, inner:]) * y[:, :inner]).float()
+    ah, al, ars = [t.to(cuda) for t in L.split_rows_rs(A)]
+    wh, wl, wsc = L.split_f16_rs(L.pad_rows(L.pack_geglu(W1, inner, ku), 256))
+    U = torch.full((2, M, ku), -1, dtype=torch.int16, device=cuda)
+    cabi.linear_h(a_hi=ah, a_lo=al, a_rs=ars, w_scale=wsc, lda=K, w_hi=wh.to(cuda), w_lo=wl.to(cuda), u_hi=U[0], u_lo=U[1], ldu=ku,
+                  M=M, N=2 * ku, K=K, epilogue=cabi.EPI_GEGLU)
+    got = _join(U[0], U[1])
+    assert (got[:, :inner] - ref).abs().max().item() < 4e-5 and torch.count_nonzero(U[:, :, inner:]).item() == 0
+    # dual-A + rope / l2norm / scale
+    Mq, N = 640, 128
+    A1, A2, Wt = _rand((Mq, K), 70, 0.3), _rand((Mq, K), 71, 40.0), _rand((1536, K), 72, 0.05)
+    ref = torch.cat([A1.double() @ Wt[:512].double().t(), A2.double() @ Wt[512:].double().t()], dim=1).float()
+    a1 = [t.to(cuda) for t in L.split_rows_rs(A1)]
+    a2 = [t.to(cuda) for t in L.split_rows_rs(A2)]
+    wh, wl, wsc = L.split_f16_rs(L.pad_rows(Wt, 256))
+    qs, ks = _rand((64,), 73, 0.5) + 1.0, _rand((64,), 74, 0.5) + 1.0
+    cos, sin = L.rope_tables(N, 64)
+    out = torch.full((Mq, 1536), float("nan"), device=cuda)
+    cabi.linear_h(a_hi=a1[0], a_lo=a1[1], a_rs=a1[2], a2_hi=a2[0], a2_lo=a2[1], a2_rs=a2[2], w_scale=wsc, n_split=512, lda=K,
+                  w_hi=wh.to(cuda), w_lo=wl.to(cuda), c=out, ldc=1536, M=Mq, N=1536, K=K, epilogue=cabi.EPI_QKV, q_scale=qs.to(cuda),
+                  k_scale=ks.to(cuda), rope_cos=cos.to(cuda), rope_sin=sin.to(cuda), qk_cols=1024, tokens=N)
+    got = out.cpu()
+    for sl, sc in ((slice(0, 512), qs), (slice(512, 1024), ks)):
+        want = (oo.l2norm(oo.apply_rope(ref[:, sl].reshape(Mq // N, N, 8, 64), cos, sin)) * sc).reshape(Mq, 512)
+        assert (got[:, sl] - want).abs().max().item() < 2e-5
+    assert ((got[:, 1024:] - ref[:, 1024:]).abs() / 40.0).max().item() < 2e-5
+    # A row map: logical rows gather from the canonical buffer, the row scales follow the same map
+    B, T, Nt, Kp = 2, 3, 64, 192
+    Xc = _rand((B * T * Nt, 512), 7) * torch.logspace(-2, 2, B * T * Nt)[:, None]
+    xh, xl, xrs = [t.to(cuda) for t in L.split_rows_rs(Xc)]
+    Wp = _rand((Kp, 512), 8, 0.05)
+    wh, wl, wsc = L.split_f16_rs(L.pad_rows(Wp, 256))
+    rows = B * (T - 1) * Nt
+    P = torch.full((rows, Kp), float("nan"), device=cuda)
+    cabi.linear_h(a_hi=xh, a_lo=xl, a_rs=xrs, w_scale=wsc, lda=512, a_seg=(T - 1) * Nt, a_seg_stride=T * Nt, a_seg_off=Nt,
+                  w_hi=wh.to(cuda), w_lo=wl.to(cuda), c=P, ldc=Kp, M=rows, N=Kp, K=512, epilogue=cabi.EPI_NONE)
+    sel = Xc.view(B, T, Nt, 512)[:, 1:].reshape(rows, 512)
+    want = (sel.double() @ Wp.double().t()).float()
+    assert ((P.cpu() - want).abs() / sel.abs().amax(dim=1, keepdim=True).clamp_min(1.0)).max().item() < 2e-5

@@ -140,8 +140,8 @@ def test_layernorm_and_patchify(cuda):
             K = ref.shape[-1]
             lw, lb = _rand((K,), 14) + 1.0, _rand((K,), 15)
             A = torch.empty(ref.numel() // K, K, device=cuda)
-            cabi.call("omt_patchify_ln", v.to(cuda), A, None, None, lw.to(cuda), lb.to(cuda), shape[0], 3, shape[2], 64, 64,
-                      8, 4, is_first, 1e-5)
+            cabi.call("omt_patchify_ln", v.to(cuda), A, None, None, None, lw.to(cuda), lb.to(cuda), shape[0], 3, shape[2], 64,
+                      64, 8, 4, is_first, 1e-5)
             want = oo.layer_norm(ref, lw, lb).reshape(-1, K)
             assert (A.cpu() - want).abs().max().item() < 5e-6
             # un-patchify is the exact inverse permutation
