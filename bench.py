@@ -204,7 +204,7 @@ def time_vq_lookup(m, M, dev, flush):
 
     def fn():
         ws.counts.zero_()
-        _cabi.call("omt_vq_search", z, eng.E, eng.e2, M, eng.n_codes, ws.idx, ws.counts, ws.vqws)
+        _cabi.call("omt_vq_search", z, eng.E, eng.e2, M, eng.n_codes, ws.idx, ws.counts)
     ms = _event_time(fn, flush)
     bytes_ = M * 8 * 4 + eng.n_codes * 8 * 4 + M * 8
     flops = 2.0 * 8 * eng.n_codes * M

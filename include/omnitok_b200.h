@@ -156,10 +156,18 @@ int omt_pre_vq(const float* x, int ldx, const float* Wt, const float* b, float* 
 
 /* Codebook.forward nearest-neighbour search (modules/codebook.py:82-86), cd == 8:
  * d[n,k] = (sum z^2 - 2 z.E_k) + sum E_k^2 in that association, idx = first argmin.
- * e2: [n_codes] precomputed sum E^2.  workspace: >= 4 * M * 8 bytes.  Also accumulates
- * counts[n_codes] (int32, caller zeroes) -- the fixed-size replacement of torch.unique (:65). */
+ * e2: [n_codes] precomputed sum E^2; n_codes % 32 == 0.  Also accumulates counts[n_codes] (int32, caller zeroes) --
+ * the fixed-size replacement of torch.unique (:65).  One launch, no workspace. */
 int omt_vq_search(const float* z, const float* E, const float* e2, int M, int n_codes,
-                  int64_t* idx, int32_t* counts, void* workspace, omt_stream_t stream);
+                  int64_t* idx, int32_t* counts, omt_stream_t stream);
+
+/* The whole VQ lookup in ONE launch: pre_vq_conv (omnitokenizer.py:248) + F.normalize (:251-252, l2 != 0) + the search
+ * above.  x [M, C] is the encoder output; z [M, 8] receives the (normalised) projection (may be NULL).  A cluster of 8
+ * CTAs shares a block of 512 rows: each CTA projects 64 of them, broadcasts z through distributed shared memory and
+ * searches all 512 against its eighth of the table; per-row minima meet again in the row's owner CTA. */
+int omt_vq_fused(const float* x, int ldx, const float* Wt, const float* b, int C, int l2, float* z,
+                 const float* E, const float* e2, int M, int n_codes, int64_t* idx, int32_t* counts,
+                 omt_stream_t stream);
 
 /* Decode-side lookup: F.embedding gather (omnitokenizer.py:270) + post_vq_conv Linear(cd, C) (:156-160).
  * If idx != NULL rows come from E[idx[r]]; else from zc[M, cd].  X[M, C] = row . Wt^T + b.

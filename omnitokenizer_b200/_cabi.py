@@ -63,7 +63,9 @@ SIGNATURES = {
     "omt_attn_temporal": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                   c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "omt_pre_vq": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "omt_vq_search": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "omt_vq_search": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "omt_vq_fused": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p]),
     "omt_post_vq": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p]),
 }
 
@@ -107,7 +109,7 @@ def _stream():
 
 
 # kernels launched per entry point (for bench.py's gpu_launches accounting)
-KERNELS_PER_CALL = {"omt_vq_search": 2}
+KERNELS_PER_CALL = {}
 launch_count = 0
 
 

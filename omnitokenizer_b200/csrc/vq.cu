@@ -1,6 +1,6 @@
-// Codebook path: pre_vq projection (+l2 normalise), exact-fp32 nearest-neighbour search with
-// the reference's  (sum z^2 - 2 z.E) + sum E^2  association and first-min tie rule, and the
-// decode-side gather + post_vq projection.
+// Codebook path: pre_vq projection (+l2 normalise) and the exact-fp32 nearest-neighbour search with the
+// reference's  (sum z^2 - 2 z.E) + sum E^2  association and first-min tie rule -- fused into one cluster
+// kernel (vq_fused_kernel) -- and the decode-side gather + post_vq projection.
 #include "omt_common.cuh"
 
 namespace omt {
@@ -53,70 +53,186 @@ __global__ void __launch_bounds__(256) pre_vq_kernel(const float* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------
-// VQ search.  grid = (row blocks, 4 code quarters); each CTA stages its quarter of the table
-// (n_codes/4 x 8 fp32, 64 KiB for 8192 codes) plus sum E^2 in shared memory, one thread per row.
-// Partial (best_d, best_idx) per quarter go to the workspace; the combine kernel takes the
-// first minimum across quarters (ascending index order == torch.argmin tie rule).
+// Fused VQ lookup: pre_vq projection + l2 normalise + || z ||^2 - 2 z E^T + || E ||^2 + argmin (+ usage histogram) in
+// ONE launch (modules/codebook.py:82-86 after omnitokenizer.py:248-252).
+//
+// A cluster of 8 CTAs owns a block of 512 rows; CTA r of the cluster
+//   A. projects rows [64 r, 64 r + 64) of the block (warp per row, the arithmetic of pre_vq_kernel) and broadcasts the
+//      8 floats of each z row into the z table of ALL 8 CTAs through distributed shared memory (and to global z);
+//   B. searches ALL 512 rows against ITS slice of the codebook (n_codes / 8 codes + their || E ||^2, staged once in
+//      shared memory with coalesced 16-byte reads): a thread owns 4 rows, so one broadcast read of a code (36 bytes)
+//      feeds 32 FMAs -- issued as 16 packed fma.rn.f32x2 over row pairs -- instead of 8 (the old kernel was
+//      shared-memory-bound at 0.27 of the FMA peak);
+//   C. sends its per-row (distance, index) to the CTA that owns the row (DSMEM again); the owner takes the first minimum
+//      over the 8 slices in ascending slice order == torch.argmin's first-min rule, writes the int64 index and bumps
+//      the histogram that replaces torch.unique (codebook.py:65).
+// Distances keep the reference association (sum z^2 - 2 z.E) + sum E^2 with the sequential fma chain of the old
+// kernel, so indices are bit-identical to it.  No workspace, no second launch.
 // ---------------------------------------------------------------------------------------
-constexpr int VQ_SPLIT = 4;
+constexpr int VQF_SLICES = 8;                 // cluster size = codebook slices
+constexpr int VQF_ROWS = 512;                 // rows per cluster
+constexpr int VQF_THREADS = 128;              // 4 rows per thread
+constexpr int VQF_OWN = VQF_ROWS / VQF_SLICES;   // rows projected / finalised per CTA
 
-__global__ void __launch_bounds__(256) vq_search_kernel(const float* __restrict__ z,
-                                                        const float* __restrict__ E,
-                                                        const float* __restrict__ e2, int M,
-                                                        int n_codes, float* __restrict__ pd,
-                                                        int* __restrict__ pi) {
-  pdl_sync();
-  extern __shared__ float4 esm[];            // [per][2] float4 + e2[per]
-  const int per = n_codes / VQ_SPLIT;
-  const int k0 = blockIdx.y * per;
-  float* e2s = reinterpret_cast<float*>(esm + 2 * per);
-  for (int i = threadIdx.x; i < 2 * per; i += blockDim.x)
-    esm[i] = reinterpret_cast<const float4*>(E + (size_t)k0 * 8)[i];
-  for (int i = threadIdx.x; i < per; i += blockDim.x) e2s[i] = e2[k0 + i];
-  __syncthreads();
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= M) return;
-  const float4 za = reinterpret_cast<const float4*>(z + (size_t)row * 8)[0];
-  const float4 zb = reinterpret_cast<const float4*>(z + (size_t)row * 8)[1];
-  // sum z^2 exactly as torch's (z**2).sum(dim=1): sequential over the 8 channels
-  float zz = za.x * za.x;
-  zz += za.y * za.y; zz += za.z * za.z; zz += za.w * za.w;
-  zz += zb.x * zb.x; zz += zb.y * zb.y; zz += zb.z * zb.z; zz += zb.w * zb.w;
-  // (2*z) @ E^T : the factor 2 is exact, fold it into z
-  const float z0 = 2.f * za.x, z1 = 2.f * za.y, z2 = 2.f * za.z, z3 = 2.f * za.w;
-  const float z4 = 2.f * zb.x, z5 = 2.f * zb.y, z6 = 2.f * zb.z, z7 = 2.f * zb.w;
-  float best = INFINITY;
-  int bi = 0;
-#pragma unroll 4
-  for (int k = 0; k < per; ++k) {
-    const float4 ea = esm[2 * k], eb = esm[2 * k + 1];
-    float dot = z0 * ea.x;
-    dot = fmaf(z1, ea.y, dot); dot = fmaf(z2, ea.z, dot); dot = fmaf(z3, ea.w, dot);
-    dot = fmaf(z4, eb.x, dot); dot = fmaf(z5, eb.y, dot); dot = fmaf(z6, eb.z, dot);
-    dot = fmaf(z7, eb.w, dot);
-    const float d = (zz - dot) + e2s[k];
-    if (d < best) { best = d; bi = k; }      // strict <  => first minimum wins
-  }
-  pd[(size_t)blockIdx.y * M + row] = best;
-  pi[(size_t)blockIdx.y * M + row] = k0 + bi;
+__device__ __forceinline__ float2 vq_ffma2(const float2 a, const float2 b, const float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<uint64_t*>(&d))
+      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)),
+        "l"(*reinterpret_cast<const uint64_t*>(&c)));
+  return d;
+}
+__device__ __forceinline__ uint32_t vq_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t vq_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void vq_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(256) vq_combine_kernel(const float* __restrict__ pd,
-                                                         const int* __restrict__ pi, int M,
-                                                         int64_t* __restrict__ idx,
-                                                         int32_t* __restrict__ counts) {
+template <bool PROJECT>       // PROJECT: rows come from x . Wt^T + b (fused pre_vq); else z is given
+__global__ void __cluster_dims__(VQF_SLICES, 1, 1) __launch_bounds__(VQF_THREADS)
+vq_fused_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ Wt, const float* __restrict__ bias, int C, int l2,
+                const float* __restrict__ z_in, float* __restrict__ z_out, const float* __restrict__ E,
+                const float* __restrict__ e2, int M, int n_codes, int64_t* __restrict__ idx, int32_t* __restrict__ counts) {
   pdl_sync();
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= M) return;
-  float best = pd[row];
-  int bi = pi[row];
+  extern __shared__ __align__(16) uint8_t vq_smem[];
+  const int per = n_codes / VQF_SLICES;
+  float4* esm = reinterpret_cast<float4*>(vq_smem);                          // [per][2] float4: this slice of the table
+  float* e2s = reinterpret_cast<float*>(esm + 2 * per);                      // [per]
+  float4* zsm = reinterpret_cast<float4*>(e2s + per);                        // [512][2] float4: the block's z rows
+  float2* part = reinterpret_cast<float2*>(zsm + 2 * VQF_ROWS);              // [8 slices][64 own rows] (distance, index bits)
+  float4* wsm = reinterpret_cast<float4*>(part + VQF_SLICES * VQF_OWN);      // PROJECT: [8][C/4] projection weights
+  const uint32_t rank = vq_cluster_rank();
+  const int row0 = (blockIdx.x / VQF_SLICES) * VQF_ROWS;
+  const int k0 = (int)rank * per;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < 2 * per; i += VQF_THREADS) esm[i] = reinterpret_cast<const float4*>(E + (size_t)k0 * 8)[i];
+  for (int i = tid; i < per; i += VQF_THREADS) e2s[i] = e2[k0 + i];
+  // ---- A. this CTA's 64 rows of z -> the z table of every CTA of the cluster
+  const uint32_t zsm_s = static_cast<uint32_t>(__cvta_generic_to_shared(zsm));
+  if (PROJECT) {
+    const int C4 = C >> 2;
+    for (int i = tid; i < 8 * C4; i += VQF_THREADS) wsm[i] = reinterpret_cast<const float4*>(Wt)[i];
+    __syncthreads();
+    for (int rr = warp; rr < VQF_OWN; rr += VQF_THREADS / 32) {
+      const int lrow = (int)rank * VQF_OWN + rr, row = row0 + lrow;
+      float acc[8];
 #pragma unroll
-  for (int s = 1; s < VQ_SPLIT; ++s) {
-    const float d = pd[(size_t)s * M + row];
-    if (d < best) { best = d; bi = pi[(size_t)s * M + row]; }
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      if (row < M) {
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+        for (int c = lane; c < C4; c += 32) {
+          const float4 xv = xr[c];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 wv = wsm[j * C4 + c];
+            acc[j] = fmaf(xv.x, wv.x, acc[j]);
+            acc[j] = fmaf(xv.y, wv.y, acc[j]);
+            acc[j] = fmaf(xv.z, wv.z, acc[j]);
+            acc[j] = fmaf(xv.w, wv.w, acc[j]);
+          }
+        }
+      }
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = warp_sum(acc[j]) + bias[j];
+        ss = fmaf(acc[j], acc[j], ss);
+      }
+      const float den = l2 ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = l2 ? acc[j] / den : acc[j];
+      if (row >= M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      }
+      if (lane < VQF_SLICES) {            // lane r writes the row into CTA r's table
+        const uint32_t dst = vq_mapa(zsm_s + (uint32_t)lrow * 32u, (uint32_t)lane);
+        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3]) : "memory");
+        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "f"(acc[4]), "f"(acc[5]), "f"(acc[6]), "f"(acc[7]) : "memory");
+      }
+      if (lane == 0 && row < M && z_out != nullptr) {
+        float4* zo = reinterpret_cast<float4*>(z_out + (size_t)row * 8);
+        zo[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        zo[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+  } else {
+    for (int i = tid; i < VQF_OWN * 2; i += VQF_THREADS) {          // this CTA's 64 rows, 2 float4 each
+      const int lrow = (int)rank * VQF_OWN + (i >> 1), row = row0 + lrow;
+      const float4 v = row < M ? reinterpret_cast<const float4*>(z_in + (size_t)row * 8)[i & 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (uint32_t r = 0; r < VQF_SLICES; ++r) {
+        const uint32_t dst = vq_mapa(zsm_s + (uint32_t)lrow * 32u + (uint32_t)(i & 1) * 16u, r);
+        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+      }
+    }
   }
-  idx[row] = bi;
-  if (counts != nullptr) atomicAdd(counts + bi, 1);
+  vq_cluster_sync();            // every CTA holds all 512 z rows (and its own table slice: __syncthreads is implied)
+
+  // ---- B. 4 rows per thread against this CTA's slice.  Rows are paired (r, r + 128) and (r + 256, r + 384) in the two
+  //         halves of packed fma.rn.f32x2 registers; each half runs exactly the scalar chain of the reference order.
+  float2 zp[2][8];           // zp[p][j] = 2 * (z[row_a][j], z[row_b][j])
+  float zz[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float4 za = zsm[2 * (tid + r * VQF_THREADS)], zb = zsm[2 * (tid + r * VQF_THREADS) + 1];
+    // sum z^2 exactly as torch's (z**2).sum(dim=1): sequential over the 8 channels
+    float s = za.x * za.x;
+    s += za.y * za.y; s += za.z * za.z; s += za.w * za.w;
+    s += zb.x * zb.x; s += zb.y * zb.y; s += zb.z * zb.z; s += zb.w * zb.w;
+    zz[r] = s;
+    const float e[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {            // (2*z) @ E^T : the factor 2 is exact, fold it into z
+      if (r & 1) zp[r >> 1][j].y = 2.f * e[j]; else zp[r >> 1][j].x = 2.f * e[j];
+    }
+  }
+  float best[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+  int bi[4] = {0, 0, 0, 0};
+#pragma unroll 2
+  for (int k = 0; k < per; ++k) {
+    const float4 ea = esm[2 * k], eb = esm[2 * k + 1];
+    const float ek = e2s[k];
+    const float ev[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      float2 dot = make_float2(zp[p][0].x * ev[0], zp[p][0].y * ev[0]);
+#pragma unroll
+      for (int j = 1; j < 8; ++j) dot = vq_ffma2(zp[p][j], make_float2(ev[j], ev[j]), dot);
+      const float d0 = (zz[2 * p] - dot.x) + ek, d1 = (zz[2 * p + 1] - dot.y) + ek;
+      if (d0 < best[2 * p]) { best[2 * p] = d0; bi[2 * p] = k; }             // strict <  => first minimum wins
+      if (d1 < best[2 * p + 1]) { best[2 * p + 1] = d1; bi[2 * p + 1] = k; }
+    }
+  }
+  // ---- C. partial minima -> the owner CTA of each row
+  const uint32_t part_s = static_cast<uint32_t>(__cvta_generic_to_shared(part));
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int lrow = tid + r * VQF_THREADS;
+    const uint32_t owner = (uint32_t)(lrow / VQF_OWN);
+    const uint32_t dst = vq_mapa(part_s + (uint32_t)((rank * VQF_OWN + (lrow % VQF_OWN)) * 8), owner);
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(dst), "f"(best[r]), "f"(__int_as_float(k0 + bi[r])) : "memory");
+  }
+  vq_cluster_sync();
+  if (tid < VQF_OWN) {
+    const int row = row0 + (int)rank * VQF_OWN + tid;
+    if (row < M) {
+      float2 b0 = part[tid];
+#pragma unroll
+      for (int s = 1; s < VQF_SLICES; ++s) {
+        const float2 c = part[s * VQF_OWN + tid];
+        if (c.x < b0.x) b0 = c;                 // ascending slices, strict <: the first minimum over the whole codebook
+      }
+      const int code = __float_as_int(b0.y);
+      idx[row] = code;
+      if (counts != nullptr) atomicAdd(counts + code, 1);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -208,29 +324,46 @@ extern "C" int omt_pre_vq(const float* x, int ldx, const float* Wt, const float*
   return OMT_OK;
 }
 
-extern "C" int omt_vq_search(const float* z, const float* E, const float* e2, int M, int n_codes,
-                             int64_t* idx, int32_t* counts, void* workspace, omt_stream_t stream) {
-  OMT_ENTER();
-  OMT_REQUIRE(z && E && e2 && idx && workspace, "omt_vq_search: null pointer");
-  OMT_REQUIRE(n_codes % VQ_SPLIT == 0 && n_codes >= VQ_SPLIT, "omt_vq_search: n_codes %% 4 != 0");
-  const int per = n_codes / VQ_SPLIT;
-  const size_t smem = (size_t)per * 36;
-  OMT_REQUIRE(smem <= 200 * 1024, "omt_vq_search: n_codes=%d too large for the shared-memory table", n_codes);
-  if (M == 0) return OMT_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    OMT_CUDA(cudaFuncSetAttribute(vq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+static int vq_launch(bool project, const float* x, int ldx, const float* Wt, const float* b, int C, int l2, const float* z_in,
+                     float* z_out, const float* E, const float* e2, int M, int n_codes, int64_t* idx, int32_t* counts,
+                     cudaStream_t st) {
+  OMT_REQUIRE(n_codes % (VQF_SLICES * 4) == 0 && n_codes >= VQF_SLICES * 4, "omt_vq: n_codes %% 32 != 0");
+  const int per = n_codes / VQF_SLICES;
+  const size_t smem = (size_t)per * 36 + VQF_ROWS * 32 + VQF_SLICES * VQF_OWN * 8 + (project ? (size_t)8 * C * 4 : 0);
+  OMT_REQUIRE(smem <= 200 * 1024, "omt_vq: n_codes=%d too large for the shared-memory table slice", n_codes);
+  static size_t set[64][2];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && smem > set[dev][project ? 1 : 0]) {
+    if (project) OMT_CUDA(cudaFuncSetAttribute(vq_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else OMT_CUDA(cudaFuncSetAttribute(vq_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set[dev][project ? 1 : 0] = smem;
   }
-  float* pd = reinterpret_cast<float*>(workspace);
-  int* pi = reinterpret_cast<int*>(pd + (size_t)VQ_SPLIT * M);
-  dim3 grid((M + 255) / 256, VQ_SPLIT);
-  OMT_CUDA(launch_k(vq_search_kernel, grid, dim3(256), smem, st, z, E, e2, M, n_codes, pd, pi));
-  OMT_LAUNCH_CHECK();
-  OMT_CUDA(launch_k(vq_combine_kernel, dim3((M + 255) / 256), dim3(256), 0, st, (const float*)pd, (const int*)pi, M, idx, counts));
+  const unsigned blocks = (unsigned)((M + VQF_ROWS - 1) / VQF_ROWS) * VQF_SLICES;
+  if (project)
+    OMT_CUDA(launch_k(vq_fused_kernel<true>, dim3(blocks), dim3(VQF_THREADS), smem, st, x, ldx, Wt, b, C, l2, z_in, z_out, E, e2, M, n_codes, idx, counts));
+  else
+    OMT_CUDA(launch_k(vq_fused_kernel<false>, dim3(blocks), dim3(VQF_THREADS), smem, st, x, ldx, Wt, b, C, l2, z_in, z_out, E, e2, M, n_codes, idx, counts));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
+}
+
+extern "C" int omt_vq_search(const float* z, const float* E, const float* e2, int M, int n_codes,
+                             int64_t* idx, int32_t* counts, omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(z && E && e2 && idx, "omt_vq_search: null pointer");
+  if (M == 0) return OMT_OK;
+  return vq_launch(false, nullptr, 0, nullptr, nullptr, 0, 0, z, nullptr, E, e2, M, n_codes, idx, counts, (cudaStream_t)stream);
+}
+
+extern "C" int omt_vq_fused(const float* x, int ldx, const float* Wt, const float* b, int C, int l2, float* z,
+                            const float* E, const float* e2, int M, int n_codes, int64_t* idx, int32_t* counts,
+                            omt_stream_t stream) {
+  OMT_ENTER();
+  OMT_REQUIRE(x && Wt && b && E && e2 && idx, "omt_vq_fused: null pointer");
+  OMT_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && C <= 1024, "omt_vq_fused: bad C/ldx");
+  if (M == 0) return OMT_OK;
+  return vq_launch(true, x, ldx, Wt, b, C, l2, nullptr, z, E, e2, M, n_codes, idx, counts, (cudaStream_t)stream);
 }
 
 extern "C" int omt_post_vq(const int64_t* idx, const float* E, const float* zc, const float* z_st_from,

@@ -86,7 +86,6 @@ class Workspace:
         self.z = torch.empty(M, cd, **f)
         self.idx = torch.empty(M, device=device, dtype=torch.int64)
         self.counts = torch.zeros(8192, device=device, dtype=torch.int32)
-        self.vqws = torch.empty(4 * M * 2, **f)
         # static I/O buffers + captured CUDA graphs of this shape
         self.x_in = None
         self.video_u8 = None
@@ -434,10 +433,12 @@ class Engine:
         self._transformer(self.enc_temporal, ws, B, Tp, h, w, temporal=True)
         cd = self.pre_w.shape[0]
         z = ws.z.view(-1)[: ws.M * cd].view(ws.M, cd)
-        _cabi.call("omt_pre_vq", ws.X, C, self.pre_w, self.pre_b, z, ws.M, C, cd, int(mode == "vq" and self.l2))
-        if mode == "vq":      # modules/codebook.py:82-86
+        if mode == "vq":      # pre_vq + l2norm + modules/codebook.py:82-86 in one cluster kernel
             ws.counts.zero_()
-            _cabi.call("omt_vq_search", z, self.E, self.e2, ws.M, self.n_codes, ws.idx, ws.counts, ws.vqws)
+            _cabi.call("omt_vq_fused", ws.X, C, self.pre_w, self.pre_b, C, int(self.l2), z, self.E, self.e2, ws.M,
+                       self.n_codes, ws.idx, ws.counts)
+        else:
+            _cabi.call("omt_pre_vq", ws.X, C, self.pre_w, self.pre_b, z, ws.M, C, cd, 0)
 
     def encode(self, x: torch.Tensor, mode: str):
         """x (B,C,T,H,W) fp32 on the device.  mode 'vq': returns (ws, dims) with ws.z (l2-normalised z),

@@ -300,16 +300,24 @@ def test_vq_path(cuda):
     e2 = (E.t() ** 2).sum(dim=0)
     idx = torch.empty(M, dtype=torch.int64, device=cuda)
     counts = torch.zeros(8192, dtype=torch.int32, device=cuda)
-    wsb = torch.empty(8 * M, device=cuda)
-    cabi.call("omt_vq_search", z, E.to(cuda), e2.to(cuda), M, 8192, idx, counts, wsb)
+    cabi.call("omt_vq_search", z, E.to(cuda), e2.to(cuda), M, 8192, idx, counts)
     assert torch.equal(idx.cpu(), out["idx"])
     assert torch.equal(counts.cpu().long(), torch.bincount(out["idx"], minlength=8192))
     # ties: duplicated codes must resolve to the FIRST index (torch.argmin rule)
     E2 = E.clone(); E2[4096:] = E[:4096]
     e22 = (E2.t() ** 2).sum(dim=0)
     counts.zero_()
-    cabi.call("omt_vq_search", z, E2.to(cuda), e22.to(cuda), M, 8192, idx, counts, wsb)
+    cabi.call("omt_vq_search", z, E2.to(cuda), e22.to(cuda), M, 8192, idx, counts)
     assert torch.equal(idx.cpu(), oo.codebook(E2, zc)["idx"]) and int(idx.max()) < 4096
+    # the fused form (projection + normalise + search in one launch) gives the same z bits and the same indices
+    for Mf in (M, 512, 1536, 37):
+        z2 = torch.full((Mf, 8), float("nan"), device=cuda)
+        idx2 = torch.full((Mf,), -1, dtype=torch.int64, device=cuda)
+        counts.zero_()
+        cabi.call("omt_vq_fused", x[:Mf].contiguous().to(cuda), C, Wp.to(cuda), bp.to(cuda), C, 1, z2, E.to(cuda), e2.to(cuda), Mf,
+                  8192, idx2, counts)
+        assert torch.equal(z2, z[:Mf]) and torch.equal(idx2.cpu(), out["idx"][:Mf])
+        assert torch.equal(counts.cpu().long(), torch.bincount(out["idx"][:Mf], minlength=8192))
     # decode-side gather + post_vq, with and without straight-through rounding
     Wq, bq = _rand((512, 8), 64, 0.3), _rand((512,), 65, 0.1)
     X = torch.empty(M, 512, device=cuda)
