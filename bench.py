@@ -262,17 +262,19 @@ def main():
     flush = torch.zeros(64 * 1024 * 1024, device=dev)      # 256 MiB > 126 MB L2
     gathered = {}
 
-    def step(x):
+    def step(x, u8=False):
+        """u8: the reconstruction leaves as uint8 frames (vqgan_eval.py's clamp / 255 / byte conversion fused into the last kernel)"""
+        dec = (lambda c: m.decode_u8(c, is_image)) if u8 else (lambda c: m.decode(c, is_image))
         if vae:      # KL path: no code indices, hence no collective; decode takes the channels-last latent (omnitokenizer.py:313)
             if x.shape[0] == 0:
                 return None
             z = m.encode(x, is_image)
-            return m.decode(z if is_image else z.permute(0, 2, 3, 4, 1), is_image)
+            return dec(z if is_image else z.permute(0, 2, 3, 4, 1))
         codes = m.encode(x, is_image)                       # an empty shard (B < world) returns an empty, right-shaped tensor
         pending = None
         if world > 1 and not os.environ.get("OMT_BENCH_NO_GATHER"):
             pending = od.all_gather_codes_async(codes, B)   # the single collective, overlapped with the local decode
-        rec = None if x.shape[0] == 0 else m.decode(codes, is_image)
+        rec = None if x.shape[0] == 0 else dec(codes)
         if pending is not None:
             gathered["codes"] = pending.wait()              # every rank now holds the full (B,T',h,w) index tensor
         return rec
@@ -314,6 +316,8 @@ def main():
     # their own streams (separate DMA engines) while step i computes; all copies are inside the timed region
     # (one event pair around the K steps, the end event waits for the last D2H).
     out_host = [torch.empty((e - s,) + shape[1:], dtype=torch.float32).pin_memory() for _ in range(2)]
+    out_host_u8 = [torch.empty((e - s, 1 if is_image else shape[2], shape[-2], shape[-1], shape[1]), dtype=torch.uint8).pin_memory()
+                   for _ in range(2)]
     e2e_steps = max(3, args.steps)
     main = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
@@ -323,7 +327,8 @@ def main():
     ev_out = [torch.cuda.Event() for _ in range(2)]
     keep = []
 
-    def e2e_run(nsteps):
+    def e2e_run(nsteps, u8=False):
+        oh = out_host_u8 if u8 else out_host
         for i in range(nsteps):
             sl = i & 1
             with torch.cuda.stream(s_in):
@@ -332,14 +337,14 @@ def main():
                 xd[sl].copy_(x_host, non_blocking=True)
                 ev_in[sl].record(s_in)
             main.wait_event(ev_in[sl])
-            rec = step(xd[sl])
+            rec = step(xd[sl], u8)
             ev_used[sl].record(main)
             if rec is not None:
                 rec.record_stream(s_out)                     # allocator: the tensor is still read by the copy stream
                 keep.append(rec)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_used[sl])
-                    out_host[sl].copy_(rec, non_blocking=True)   # out_host[sl] of step i-2 was drained on this same stream
+                    oh[sl].copy_(rec, non_blocking=True)         # oh[sl] of step i-2 was drained on this same stream
                     ev_out[sl].record(s_out)
             if len(keep) > 3:
                 keep.pop(0)
@@ -368,10 +373,21 @@ def main():
     s_in.synchronize(); s_out.synchronize()
     clocks = sampler.stop() if sampler else None
     t2_ms = t_a.elapsed_time(t_b)
-    tt = torch.tensor([t_ms, t2_ms], device=dev, dtype=torch.float64)
+    # same pipeline with the uint8 epilogue: D2H is a quarter of the bytes (what vqgan_eval.py's metrics consume)
+    e2e_run(2, u8=True)
+    barrier()
+    flush.add_(1.0)
+    u_a, u_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u_a.record(main)
+    e2e_run(e2e_steps, u8=True)
+    u_b.record(main)
+    barrier()
+    s_in.synchronize(); s_out.synchronize()
+    t3_ms = u_a.elapsed_time(u_b)
+    tt = torch.tensor([t_ms, t2_ms, t3_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms, t2_ms = tt.tolist()
+    t_ms, t2_ms, t3_ms = tt.tolist()
     frames = B * frames_per_sample
     value = frames * args.steps / (t_ms / 1e3)
     e2e = frames * e2e_steps / (t2_ms / 1e3)
@@ -418,7 +434,10 @@ def main():
             "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": out_host[0].numel() * 4, "ms_per_step": round(t2_ms / e2e_steps, 3),
                     "steps": e2e_steps, "pipeline": "H2D / compute / D2H of consecutive steps overlap on 3 streams",
-                    "host_link": link},
+                    "host_link": link,
+                    "u8": {"value": round(frames * e2e_steps / (t3_ms / 1e3), 2), "unit": "frames/s",
+                           "d2h_bytes_per_step": out_host_u8[0].numel(), "ms_per_step": round(t3_ms / e2e_steps, 3),
+                           "what": "reconstruction fetched as uint8 frames (decode_u8: clamp(x+0.5,0,1)*255 fused into un-patchify)"}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
         if gather_ok is not None:
