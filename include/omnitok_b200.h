@@ -45,7 +45,8 @@ int omt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* GEMM epilogue selectors */
 #define OMT_EPI_NONE 0
 #define OMT_EPI_GEGLU 1   /* packed columns (2j, 2j+1) = (value, gate): C[:, j] = gelu_erf(gate) * value */
-#define OMT_EPI_QKV 2     /* omt_linear2 only: rope + l2norm + scale on the q / k heads (attention.py:417-437) */
+#define OMT_EPI_QKV 2     /* dual-A forms: rope + l2norm + scale on the q / k heads (attention.py:417-437) */
+#define OMT_EPI_QKV_PLANES 3   /* omt_linear_h: the same, but q / k / v leave as fp16 operand planes for omt_attn_spatial_h */
 
 /* GEMM math selectors */
 #define OMT_MATH_FP32 0      /* CUDA-core FFMA, exact fp32 (parity anchor) */
@@ -136,6 +137,14 @@ int omt_attn_spatial(const float* q, int ldq, const float* k, int ldk, const flo
                      float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, int n_seq, int N, int heads, float scale,
                      omt_stream_t stream);
 
+/* omt_attn_spatial on the operand planes written by omt_linear_h(OMT_EPI_QKV_PLANES): tcgen05 kind::f16 core, Q / P in
+ * tensor memory, K / V tiles straight from TMA (V as an MN-major operand: no transpose), N % 128 == 0.
+ * qk_plane_scale = q_plane_scale * k_plane_scale; vinv [heads][n_seq * N]. */
+int omt_attn_spatial_h(const uint16_t* q_hi, const uint16_t* q_lo, int ldq, const uint16_t* k_hi, const uint16_t* k_lo, int ldk,
+                       const uint16_t* v_hi, const uint16_t* v_lo, int ldv, const float* vinv, float qk_plane_scale,
+                       float* o, uint16_t* o_hi, uint16_t* o_lo, int ldo, int n_seq, int N, int heads, float scale,
+                       omt_stream_t stream);
+
 /* 8x8 (ws x ws, ws*ws == 64) window attention with relative position bias (attention.py:254-286):
  * o = softmax(scale * q k^T + bias[head]) v within each window of the (h, w) token grid.
  * bias: [heads, 64, 64] already gathered from the 225-entry table. */
@@ -200,6 +209,11 @@ typedef struct omt_linear_h_args {
   int epilogue;
   const float* q_scale; const float* k_scale; const float* rope_cos; const float* rope_sin;   /* OMT_EPI_QKV, as omt_linear2 */
   int qk_cols, tokens;
+  /* OMT_EPI_QKV_PLANES: output planes u_hi / u_lo [M, N] (ldu): q / k heads multiplied by the static powers of two
+   * q_plane_scale / k_plane_scale (|q| <= max|q_scale| after l2norm, so the bound is exact), v heads scaled per
+   * (row, head) with the inverse scales written to vinv [N_v / 64][M]; lo planes unscaled. */
+  float q_plane_scale, k_plane_scale;
+  float* vinv;
 } omt_linear_h_args;
 
 /* Same contract as omt_linear / omt_linear2 (nn.Linear + the fused epilogues) on operand planes. */

@@ -14,7 +14,7 @@ import torch
 _LIB_NAME = "libomnitok_b200.so"
 _lib = None
 
-EPI_NONE, EPI_GEGLU, EPI_QKV = 0, 1, 2
+EPI_NONE, EPI_GEGLU, EPI_QKV, EPI_QKV_PLANES = 0, 1, 2, 3
 MATH_FP32, MATH_3XTF32, MATH_F16X3 = 0, 1, 3
 ABI_VERSION = 2
 
@@ -31,7 +31,8 @@ class LinearHArgs(ctypes.Structure):
                 ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int),
                 ("epilogue", c_int),
                 ("q_scale", c_void_p), ("k_scale", c_void_p), ("rope_cos", c_void_p), ("rope_sin", c_void_p),
-                ("qk_cols", c_int), ("tokens", c_int)]
+                ("qk_cols", c_int), ("tokens", c_int),
+                ("q_plane_scale", c_float), ("k_plane_scale", c_float), ("vinv", c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/omnitok_b200.h one to one
@@ -58,6 +59,8 @@ SIGNATURES = {
                             c_int, c_void_p]),
     "omt_attn_spatial": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_int, c_int, c_float, c_void_p]),
+    "omt_attn_spatial_h": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                   c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "omt_attn_window": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "omt_attn_temporal": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,

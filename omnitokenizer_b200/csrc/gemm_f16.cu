@@ -65,6 +65,9 @@ struct HArgs {
   uint16_t* u_hi; uint16_t* u_lo; int ldu;    // GEGLU: split planes of U[M, N/2]
   const float* rope_cos; const float* rope_sin; const float* q_scale; const float* k_scale;
   int qk_cols; int tokens;
+  // OMT_EPI_QKV_PLANES: q / k / v leave as fp16 operand planes for the attention core (attention_f16.cu)
+  float q_ps, k_ps;                           // static plane scales of the q and k heads (powers of two)
+  float* vinv;                                // [v heads][M]: inverse per-(row, head) scale of the v planes
 };
 
 // Tile raster: clusters walk the tiles in groups of G = num_clusters m-blocks; inside a group all clusters take the
@@ -91,7 +94,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
                 const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-                const __grid_constant__ CUtensorMap tmC, const HArgs g) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPh,
+                const __grid_constant__ CUtensorMap tmPl, const HArgs g) {
   using C_ = Cfg<BN, NACC>;
   constexpr int W_BYTES = C_::W_BYTES, STAGE_BYTES = C_::STAGE_BYTES, STAGES = C_::STAGES, NBUF = C_::NBUF;
   static_assert(NBUF * NACC * BN <= 512, "TMEM: NACC accumulators of BN columns, NBUF buffers");
@@ -287,7 +291,23 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         }
       };
 
-      if constexpr (EPI == OMT_EPI_QKV) {
+      // a 32-row x 64-column fp16 plane tile (one head of this warp's rows): words w[32] of this lane's row -> slab -> TMA
+      auto store_plane = [&](const CUtensorMap* map, int n, const uint32_t (&w)[32]) {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + sw128(lane, c4)), "r"(w[4 * c4]), "r"(w[4 * c4 + 1]),
+                       "r"(w[4 * c4 + 2]), "r"(w[4 * c4 + 3]) : "memory");
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && mw < g.M) {
+          tma_store_2d(map, slab, n, mw);
+          bulk_commit();
+        }
+      };
+
+      if constexpr (EPI == OMT_EPI_QKV || EPI == OMT_EPI_QKV_PLANES) {
         // ---- q / k heads: rope + l2norm + per-dim scale (attention.py:417-421, 435-437); a head = two chunks, all
         //      64 values of a row live in one lane, so the norm is thread-local
 #pragma unroll
@@ -346,8 +366,30 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                 vb[4 * i + 2] = vb[4 * i + 2] * inv * sb.z; vb[4 * i + 3] = vb[4 * i + 3] * inv * sb.w;
               }
             }
-            store_box(nh, va);
-            if (nh + 32 < g.N) store_box(nh + 32, vb);
+            if constexpr (EPI == OMT_EPI_QKV) {
+              store_box(nh, va);
+              if (nh + 32 < g.N) store_box(nh + 32, vb);
+            } else {
+              // operand planes for the attention core: q / k with the layer's static power-of-two scale, v scaled per
+              // (row, head) -- this lane holds the whole head of its row -- with the inverse scale kept in vinv
+              float sc = nh < g.qk_cols / 2 ? g.q_ps : g.k_ps;
+              if (nh >= g.qk_cols) {
+                float mx = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(fabsf(va[j]), fabsf(vb[j])));
+                float inv;
+                row_scale(mx, sc, inv);
+                if (row_ok) g.vinv[(size_t)((nh - g.qk_cols) >> 6) * g.M + m] = inv;
+              }
+              uint32_t wh[32], wl[32];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                split2u(va[2 * i] * sc, va[2 * i + 1] * sc, wh[i], wl[i]);
+                split2u(vb[2 * i] * sc, vb[2 * i + 1] * sc, wh[16 + i], wl[16 + i]);
+              }
+              store_plane(&tmPh, nh, wh);
+              store_plane(&tmPl, nh, wl);
+            }
           }
         }
       } else if constexpr (EPI == OMT_EPI_GEGLU) {
@@ -472,7 +514,7 @@ static int launch(const CUtensorMap* maps, const HArgs& g, cudaStream_t st) {
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
-  OMT_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], g));
+  OMT_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], maps[8], g));
   return OMT_OK;
 }
 
@@ -496,7 +538,7 @@ int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   if (a.a2_hi != nullptr) OMT_REQUIRE(a.n_split > 0 && a.n_split % 256 == 0, "omt_linear_h: n_split=%d must be a multiple of 256", a.n_split);
   const int n_pad = (a.N + 255) / 256 * 256;
   const CUtensorMapDataType dt_hi = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, dt_lo = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap maps[7];
+  CUtensorMap maps[9];
   int rc;
   if ((rc = row_map(&maps[0], dt_hi, 2, a.a_hi, a.lda, a.M, a.K, a.a_seg, a.a_seg_stride, a.a_seg_off, BK, 64))) return rc;
   if ((rc = row_map(&maps[1], dt_lo, 2, a.a_lo, a.lda, a.M, a.K, a.a_seg, a.a_seg_stride, a.a_seg_off, BK, 64))) return rc;
@@ -510,8 +552,16 @@ int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
     if ((rc = encode_map(&maps[4], dt_hi, a.w_hi, 2, dims, strides, box))) return rc;
     if ((rc = encode_map(&maps[5], dt_lo, a.w_lo, 2, dims, strides, box))) return rc;
   }
+  maps[7] = maps[0]; maps[8] = maps[0];
   if (a.epilogue == OMT_EPI_GEGLU) {
     maps[6] = maps[0];      // unused by the GEGLU epilogue (direct stores of the U planes)
+  } else if (a.epilogue == OMT_EPI_QKV_PLANES) {
+    maps[6] = maps[0];
+    cuuint64_t dims[2] = {(cuuint64_t)a.N, (cuuint64_t)a.M};
+    cuuint64_t strides[1] = {(cuuint64_t)a.ldu * 2};
+    cuuint32_t box[2] = {64, 32};
+    if ((rc = encode_map(&maps[7], dt_hi, a.u_hi, 2, dims, strides, box))) return rc;
+    if ((rc = encode_map(&maps[8], dt_lo, a.u_lo, 2, dims, strides, box))) return rc;
   } else {
     if ((rc = row_map(&maps[6], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.c, a.ldc, a.M, a.N, a.c_seg, a.c_seg_stride, a.c_seg_off, 32, 32))) return rc;
   }
@@ -527,8 +577,10 @@ int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   g.u_hi = a.u_hi; g.u_lo = a.u_lo; g.ldu = a.ldu;
   g.rope_cos = a.rope_cos; g.rope_sin = a.rope_sin; g.q_scale = a.q_scale; g.k_scale = a.k_scale;
   g.qk_cols = a.qk_cols; g.tokens = a.tokens > 0 ? a.tokens : 1;
+  g.q_ps = a.q_plane_scale; g.k_ps = a.k_plane_scale; g.vinv = a.vinv;
 #define OMT_F16_LAUNCH(EPI_) (rs ? launch<256, 1, EPI_>(maps, g, st) : (BN == 256 ? launch<256, 2, EPI_>(maps, g, st) : launch<128, 2, EPI_>(maps, g, st)))
   if (a.epilogue == OMT_EPI_QKV) return OMT_F16_LAUNCH(OMT_EPI_QKV);
+  if (a.epilogue == OMT_EPI_QKV_PLANES) return OMT_F16_LAUNCH(OMT_EPI_QKV_PLANES);
   if (a.epilogue == OMT_EPI_GEGLU) return OMT_F16_LAUNCH(OMT_EPI_GEGLU);
   return OMT_F16_LAUNCH(OMT_EPI_NONE);
 #undef OMT_F16_LAUNCH
@@ -546,8 +598,13 @@ extern "C" int omt_linear_h(const omt_linear_h_args* a, omt_stream_t stream) {
   OMT_REQUIRE(a->a2_hi == nullptr || ((a->a_rs == nullptr) == (a->a2_rs == nullptr)), "omt_linear_h: both A operands must use the same plane format");
   OMT_REQUIRE(a->a_rs == nullptr || (a->w_scale > 0.f && a->w_scale < 3.0e38f), "omt_linear_h: row-scaled planes need the weight scale");
   OMT_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "omt_linear_h: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
-  OMT_REQUIRE(a->epilogue == OMT_EPI_NONE || a->epilogue == OMT_EPI_GEGLU || a->epilogue == OMT_EPI_QKV, "omt_linear_h: unknown epilogue %d", a->epilogue);
-  if (a->epilogue == OMT_EPI_GEGLU) {
+  OMT_REQUIRE(a->epilogue == OMT_EPI_NONE || a->epilogue == OMT_EPI_GEGLU || a->epilogue == OMT_EPI_QKV || a->epilogue == OMT_EPI_QKV_PLANES,
+              "omt_linear_h: unknown epilogue %d", a->epilogue);
+  if (a->epilogue == OMT_EPI_QKV_PLANES) {
+    OMT_REQUIRE(a->u_hi && a->u_lo && a->vinv && a->ldu % 8 == 0 && a->q_plane_scale > 0.f && a->k_plane_scale > 0.f,
+                "omt_linear_h: the QKV-planes epilogue writes u_hi / u_lo [M, N] (ldu %% 8 == 0), vinv and needs the q / k plane scales");
+    OMT_REQUIRE(((uintptr_t)a->u_hi | (uintptr_t)a->u_lo) % 16 == 0, "omt_linear_h: output planes must be 16-byte aligned");
+  } else if (a->epilogue == OMT_EPI_GEGLU) {
     OMT_REQUIRE(a->u_hi && a->u_lo && a->ldu % 8 == 0 && a->residual == nullptr && a->bias == nullptr,
                 "omt_linear_h: GEGLU writes the U planes (ldu %% 8 == 0) and takes no bias / residual");
     OMT_REQUIRE(((uintptr_t)a->u_hi | (uintptr_t)a->u_lo) % 16 == 0, "omt_linear_h: U planes must be 16-byte aligned");
@@ -556,7 +613,7 @@ extern "C" int omt_linear_h(const omt_linear_h_args* a, omt_stream_t stream) {
     OMT_REQUIRE(a->residual == nullptr || (a->ldr % 4 == 0 && (uintptr_t)a->residual % 16 == 0), "omt_linear_h: bad residual");
     OMT_REQUIRE(a->bias == nullptr || (uintptr_t)a->bias % 16 == 0, "omt_linear_h: bias must be 16-byte aligned");
   }
-  if (a->epilogue == OMT_EPI_QKV) {
+  if (a->epilogue == OMT_EPI_QKV || a->epilogue == OMT_EPI_QKV_PLANES) {
     OMT_REQUIRE(a->q_scale && a->k_scale && a->qk_cols > 0 && a->qk_cols % 128 == 0 && a->qk_cols <= a->N && a->tokens > 0 &&
                 a->tokens % 32 == 0, "omt_linear_h: bad q/k preparation arguments");
     OMT_REQUIRE((a->rope_cos == nullptr) == (a->rope_sin == nullptr), "omt_linear_h: cos/sin must both be given");

@@ -79,6 +79,8 @@ class Workspace:
             self.XNp, self.XSp = Planes(device, M, C, True), Planes(device, M, C, True)     # LayerNorm sees whole rows
             self.Op, self.Up = Planes(device, M, C), Planes(device, M, ku)                  # attention heads / GEGLU tiles do not
             self.Pp = Planes(device, M, kmax, True)
+            self.QKVp = Planes(device, M, 3 * C)     # q | k | v operand planes for the f16 attention core (QKV GEMM epilogue)
+            self.vinv = torch.empty(C // 64, M, device=device, dtype=torch.float32)   # inverse (row, head) scales of the v planes
         else:
             self.XN = torch.empty(M, C, **f)
             self.O = torch.empty(M, C, **f)
@@ -129,6 +131,8 @@ class Engine:
             raise NotImplementedError(f"--codebook_dim {self.cd}: the VQ search / post_vq kernels are specialised for "
                                       "codebook_dim 8 (every shipped config); VAE mode takes 8 latent channels as well")
         self.planes = self.math == _cabi.MATH_F16X3
+        # spatial attention core on fp16 operand planes (attention_f16.cu); 0 = the 3xTF32 core on the fp32 QKV buffer
+        self.attn_f16 = self.planes and os.environ.get("OMT_ATTN_F16", "0") == "1"
         if a.attn_dropout != 0 or a.ff_dropout != 0:
             raise NotImplementedError("non-zero dropout reaches SDPA even in eval in the reference (attention.py:451); rejected")
         self._ws: Dict[Tuple, Workspace] = {}
@@ -156,6 +160,8 @@ class Engine:
             ap = lp + ".1"
             d["norm_g"], d["norm_b"] = f32(sd[ap + ".norm.gamma"]), f32(sd[ap + ".norm.beta"])
             d["q_scale"], d["k_scale"] = f32(sd[ap + ".q_scale"]), f32(sd[ap + ".k_scale"])
+            # after l2norm every |q_d| <= |q_scale_d|: one exact power of two per layer puts the q / k planes in fp16 range
+            d["q_ps"], d["k_ps"] = L.pow2_scale(float(d["q_scale"].abs().max())), L.pow2_scale(float(d["k_scale"].abs().max()))
             # [Wq; Wkv] stacked: one dual-A GEMM writes q | k | v into the QKV buffer
             d["to_qkv"] = PL(torch.cat([sd[ap + ".to_q.weight"], sd[ap + ".to_kv.weight"]], dim=0), None, row_scaled=True)
             d["to_out"] = lin(ap + ".to_out", bias=False)
@@ -269,7 +275,8 @@ class Engine:
                    c_map[2], M, lin.n, lin.k, lin.bias if bias else None, residual, ldr, epi, lin.math)
 
     def _linear_h(self, A: Planes, lin: PackedLinear, M, *, C=None, ldc=0, U: Optional[Planes] = None, A2: Optional[Planes] = None,
-                  n_split=0, a_map=(0, 0, 0), c_map=(0, 0, 0), residual=None, ldr=0, epi=_cabi.EPI_NONE, qk=None):
+                  n_split=0, a_map=(0, 0, 0), c_map=(0, 0, 0), residual=None, ldr=0, epi=_cabi.EPI_NONE, qk=None,
+                  planes=None):
         """nn.Linear on operand planes (tcgen05 f16x3).  U: GEGLU output planes; qk: (q_scale, k_scale, cos, sin, qk_cols, tokens)."""
         if (A.rs is not None) != lin.row_scaled:
             raise RuntimeError("operand planes and weight planes are in different f16x3 forms (row-scaled vs 2^11-scaled lo)")
@@ -284,6 +291,8 @@ class Engine:
             kw.update(u_hi=U.hi, u_lo=U.lo, ldu=U.ld)
         if qk is not None:
             kw.update(q_scale=qk[0], k_scale=qk[1], rope_cos=qk[2], rope_sin=qk[3], qk_cols=qk[4], tokens=qk[5])
+        if planes is not None:      # EPI_QKV_PLANES: U = the q | k | v planes, (q plane scale, k plane scale, vinv)
+            kw.update(q_plane_scale=planes[0], k_plane_scale=planes[1], vinv=planes[2])
         _cabi.linear_h(**kw)
 
     def _ln(self, x, y, g, b, M, C=None, seg=(0, 0, 0)):
@@ -316,7 +325,13 @@ class Engine:
                 cos = sin = None
                 if (not temporal) and self.rope:
                     cos, sin = self._table(("rope", N), lambda: L.rope_tables(N, self.dh))
-                if H:
+                f16_core = H and self.attn_f16 and (not temporal) and N % 128 == 0
+                if f16_core:
+                    self._ln_h(ws.X, ws.XNp, lyr["norm_g"], lyr["norm_b"], M, xp=ws.XSp)
+                    self._linear_h(ws.XNp, wq, M, U=ws.QKVp, A2=ws.XSp, n_split=C, epi=_cabi.EPI_QKV_PLANES,
+                                   qk=(lyr["q_scale"], lyr["k_scale"], cos, sin, 2 * C, N),
+                                   planes=(lyr["q_ps"], lyr["k_ps"], ws.vinv))
+                elif H:
                     self._ln_h(ws.X, ws.XNp, lyr["norm_g"], lyr["norm_b"], M, xp=ws.XSp)
                     self._linear_h(ws.XNp, wq, M, C=q_ptr, ldc=ld3, A2=ws.XSp, n_split=C, epi=_cabi.EPI_QKV,
                                    qk=(lyr["q_scale"], lyr["k_scale"], cos, sin, 2 * C, N))
@@ -330,7 +345,11 @@ class Engine:
                                    None, None, None, None, 0, 0)
                         _cabi.call("omt_qk_prep", q_ptr, ld3, k_ptr, ld3, lyr["q_scale"], lyr["k_scale"], cos, sin, M, N,
                                    self.heads)
-                if temporal:
+                if f16_core:
+                    ph, pl = ws.QKVp.hi.data_ptr(), ws.QKVp.lo.data_ptr()
+                    _cabi.call("omt_attn_spatial_h", ph, pl, ld3, ph + 2 * C, pl + 2 * C, ld3, ph + 4 * C, pl + 4 * C, ld3,
+                               ws.vinv, lyr["q_ps"] * lyr["k_ps"], None, o_hi, o_lo, C, B * T, N, self.heads, 8.0)
+                elif temporal:
                     _cabi.call("omt_attn_temporal", q_ptr, ld3, k_ptr, ld3, v_ptr, ld3, o, o_hi, o_lo, C, B, T, N,
                                self.heads, 8.0, int(self.causal_attn))
                 else:

@@ -97,6 +97,13 @@ def split_f16_rs(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, float]:
     return hi.contiguous(), lo.contiguous(), 2.0 ** -e
 
 
+def pow2_scale(bound: float) -> float:
+    """The power of two that maps values bounded by `bound` into [2^14, 2^15) (fp16 range with headroom); 1.0 for 0."""
+    if not (bound > 0.0) or not math.isfinite(bound):
+        return 1.0
+    return 2.0 ** max(-100, min(100, 14 - math.floor(math.log2(bound))))
+
+
 def split_rows_rs(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Row-scaled form of an activation matrix, the host twin of csrc/omt_common.cuh row_scale(): per row the power of two
     that puts the largest magnitude in [2^14, 2^15).  Returns (hi, lo, inverse row scales [rows])."""

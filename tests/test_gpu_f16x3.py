@@ -311,3 +311,75 @@ def test_linear_h_row_scaled_epilogues(cuda):
     sel = Xc.view(B, T, Nt, 512)[:, 1:].reshape(rows, 512)
     want = (sel.double() @ Wp.double().t()).float()
     assert ((P.cpu() - want).abs() / sel.abs().amax(dim=1, keepdim=True).clamp_min(1.0)).max().item() < 2e-5
+
+
+def _static_planes(x, ps):
+    xs = x.float() * ps
+    hi = xs.clamp(-65504, 65504).half()
+    return hi, (xs - hi.float()).half()
+
+
+@pytest.mark.parametrize("N", [128, 256, 1024])
+def test_attn_spatial_h(cuda, N):
+    """tcgen05 kind::f16 attention core on operand planes (Q / P in tensor memory, V as MN-major B) vs fp64 softmax;
+    q, k unit-norm x scale as the QKV epilogue leaves them, v rows of very different magnitude."""
+    cabi = _cabi(0)
+    from omnitokenizer_b200 import layout as L
+    nseq, H = 3, 8
+    M = nseq * N
+    g = torch.Generator().manual_seed(40 + N)
+    q = torch.nn.functional.normalize(torch.randn(M, H, 64, generator=g), dim=-1) * (torch.rand(64, generator=g) + 0.5)
+    k = torch.nn.functional.normalize(torch.randn(M, H, 64, generator=g), dim=-1) * (torch.rand(64, generator=g) + 0.5)
+    v = torch.randn(M, H, 64, generator=g) * torch.logspace(-2, 2, M)[torch.randperm(M, generator=g)][:, None, None]
+    qs, ks = L.pow2_scale(float(q.abs().max())), L.pow2_scale(float(k.abs().max()))
+    qh, ql = _static_planes(q.reshape(M, 512), qs)
+    kh, kl = _static_planes(k.reshape(M, 512), ks)
+    vh, vl, vinv = L.split_rows_rs(v.reshape(M * H, 64))
+    vh, vl, vinv = vh.reshape(M, 512), vl.reshape(M, 512), vinv.reshape(M, H).t().contiguous()
+    dev = lambda t: t.contiguous().to(cuda)
+    qh, ql, kh, kl, vh, vl, vinv = map(dev, (qh, ql, kh, kl, vh, vl, vinv))
+    o = torch.full((M, 512), float("nan"), device=cuda)
+    cabi.call("omt_attn_spatial_h", qh, ql, 512, kh, kl, 512, vh, vl, 512, vinv, qs * ks, o, None, None, 512, nseq, N, H, 8.0)
+    torch.cuda.synchronize()
+    qq, kk, vv = (t.view(nseq, N, H, 64).permute(0, 2, 1, 3).double() for t in (q, k, v))
+    want = (torch.softmax((qq @ kk.transpose(-1, -2)) * 8.0, dim=-1) @ vv).permute(0, 2, 1, 3).reshape(M, 512).float()
+    rel = ((o.cpu() - want).abs() / want.abs().amax(dim=1, keepdim=True).clamp_min(1e-3)).max().item()
+    assert rel < 2e-5, f"f16 attention core N={N}: max error relative to the row magnitude {rel:.2e}"
+    op = torch.zeros(2, M, 512, dtype=torch.int16, device=cuda)
+    cabi.call("omt_attn_spatial_h", qh, ql, 512, kh, kl, 512, vh, vl, 512, vinv, qs * ks, None, op[0], op[1], 512, nseq, N, H, 8.0)
+    assert (_join(op[0], op[1]) - o.cpu()).abs().max().item() <= 2.0 ** -21 * o.abs().max().item()
+
+
+def test_linear_h_qkv_planes(cuda):
+    """The QKV GEMM epilogue that feeds the f16 attention core: q / k planes with static power-of-two scales, v planes
+    scaled per (row, head) with vinv -- reconstructed values vs the fp32-output epilogue of the same GEMM."""
+    cabi = _cabi(0)
+    from omnitokenizer_b200 import layout as L
+    M, K, N = 640, 512, 128
+    A1, A2, Wt = _rand((M, K), 70, 0.3), _rand((M, K), 71, 5.0), _rand((1536, K), 72, 0.05)
+    A2 = A2 * torch.logspace(-2, 1, M)[:, None]
+    a1 = [t.to(cuda) for t in L.split_rows_rs(A1)]
+    a2 = [t.to(cuda) for t in L.split_rows_rs(A2)]
+    wh, wl, wsc = L.split_f16_rs(L.pad_rows(Wt, 256))
+    qsc, ksc = _rand((64,), 73, 0.5) + 1.0, _rand((64,), 74, 0.5) + 1.0
+    cos, sin = L.rope_tables(N, 64)
+    common = dict(a_hi=a1[0], a_lo=a1[1], a_rs=a1[2], a2_hi=a2[0], a2_lo=a2[1], a2_rs=a2[2], w_scale=wsc, n_split=512, lda=K,
+                  w_hi=wh.to(cuda), w_lo=wl.to(cuda), M=M, N=1536, K=K, q_scale=qsc.to(cuda), k_scale=ksc.to(cuda),
+                  rope_cos=cos.to(cuda), rope_sin=sin.to(cuda), qk_cols=1024, tokens=N)
+    ref = torch.full((M, 1536), float("nan"), device=cuda)
+    cabi.linear_h(c=ref, ldc=1536, epilogue=cabi.EPI_QKV, **common)
+    P = torch.full((2, M, 1536), -1, dtype=torch.int16, device=cuda)
+    vinv = torch.zeros(8, M, device=cuda)
+    qps, kps = L.pow2_scale(float(qsc.abs().max())), L.pow2_scale(float(ksc.abs().max()))
+    cabi.linear_h(u_hi=P[0], u_lo=P[1], ldu=1536, epilogue=cabi.EPI_QKV_PLANES, q_plane_scale=qps, k_plane_scale=kps, vinv=vinv,
+                  **common)
+    torch.cuda.synchronize()
+    val = P[0].cpu().view(torch.float16).float() + P[1].cpu().view(torch.float16).float()
+    ref = ref.cpu()
+    assert (val[:, :512] / qps - ref[:, :512]).abs().max().item() <= 2.0 ** -21 * float(qsc.abs().max())
+    assert (val[:, 512:1024] / kps - ref[:, 512:1024]).abs().max().item() <= 2.0 ** -21 * float(ksc.abs().max())
+    vv = val[:, 1024:].view(M, 8, 64) * vinv.cpu().t()[:, :, None]
+    rv = ref[:, 1024:].view(M, 8, 64)
+    assert ((vv - rv).abs() <= 2.0 ** -21 * rv.abs().amax(dim=-1, keepdim=True)).all()
+    top = P[0].cpu().view(torch.float16).float()[:, 1024:].view(M, 8, 64).abs().amax(dim=-1)
+    assert (top >= 2.0 ** 14).all() and (top <= 2.0 ** 15).all()

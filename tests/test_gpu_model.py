@@ -18,6 +18,13 @@ def _math_modes():
     return [m for m in os.environ.get("OMT_TEST_MATH", "fp32,3xtf32,f16x3").split(",") if m]
 
 
+@pytest.fixture(autouse=True, params=[m for m in os.environ.get("OMT_TEST_ATTN_F16", "0,1").split(",") if m])
+def _attention_core(request, monkeypatch):
+    """every model-level test runs with the 3xTF32 attention core and with the fp16-plane core (f16x3 math only uses it)"""
+    monkeypatch.setenv("OMT_ATTN_F16", request.param)
+    yield
+
+
 @pytest.mark.parametrize("math", _math_modes())
 @pytest.mark.parametrize("name", ["img64", "vid5x64", "vid9x128_b2", "img256_cfg1", "cnn_vid5x64"])
 def test_vq_encode_decode_matches_golden(cuda, name, math):
