@@ -214,6 +214,10 @@ typedef struct omt_linear_h_args {
    * (row, head) with the inverse scales written to vinv [N_v / 64][M]; lo planes unscaled. */
   float q_plane_scale, k_plane_scale;
   float* vinv;
+  /* statically bounded operands: a_rs_uniform > 0 (with a_rs == NULL) = row-scaled form with ONE inverse scale for all rows;
+   * u_scale > 0 (OMT_EPI_GEGLU) = write the U planes in that form, multiplied by u_scale (|U| * u_scale < 65504 is the
+   * caller's guarantee: |gelu(g) * a| <= |g| |a| and both are bounded through the LayerNorm in front of the GEMM). */
+  float a_rs_uniform, u_scale;
 } omt_linear_h_args;
 
 /* Same contract as omt_linear / omt_linear2 (nn.Linear + the fused epilogues) on operand planes. */

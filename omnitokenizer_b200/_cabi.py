@@ -32,7 +32,8 @@ class LinearHArgs(ctypes.Structure):
                 ("epilogue", c_int),
                 ("q_scale", c_void_p), ("k_scale", c_void_p), ("rope_cos", c_void_p), ("rope_sin", c_void_p),
                 ("qk_cols", c_int), ("tokens", c_int),
-                ("q_plane_scale", c_float), ("k_plane_scale", c_float), ("vinv", c_void_p)]
+                ("q_plane_scale", c_float), ("k_plane_scale", c_float), ("vinv", c_void_p),
+                ("a_rs_uniform", c_float), ("u_scale", c_float)]
 
 
 # name -> (restype, argtypes); mirrors include/omnitok_b200.h one to one

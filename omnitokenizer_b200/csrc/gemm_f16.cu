@@ -58,7 +58,9 @@ struct HArgs {
   int num_m_blk, num_n_blk, n_split;
   int a_seg, a_seg_stride, a_seg_off;         // A row map (the TMA strides live in the tensor maps; the epilogue needs it for a_rs)
   const float* a_rs; const float* a2_rs;      // NACC == 1: inverse row scales of the A planes (second: dual-A columns >= n_split)
+  float a_rs_uniform;                         // NACC == 1 with a_rs == NULL: one inverse scale for every row (statically bounded A)
   float w_scale;                              // NACC == 1: inverse scale of the W planes
+  float u_scale;                              // GEGLU: > 0 -> U planes in the static-scaled form (unscaled lo), else 2^11-scaled lo
   int c_seg, c_seg_stride, c_seg_off;         // C / residual row map
   const float* bias;
   const float* residual; int ldr;
@@ -238,7 +240,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       float out_scale = 1.0f;                                          // row-scaled form: exact inverse of the operand scales
       if (NACC == 1) {
         const float* rs = (n_blk * BN >= g.n_split) ? g.a2_rs : g.a_rs;
-        out_scale = g.w_scale * (row_ok ? __ldg(rs + map_row(m, g.a_seg, g.a_seg_stride, g.a_seg_off)) : 1.0f);
+        out_scale = g.w_scale * (rs == nullptr ? g.a_rs_uniform : (row_ok ? __ldg(rs + map_row(m, g.a_seg, g.a_seg_stride, g.a_seg_off)) : 1.0f));
       }
 
       // residual row segments (8 x 16 bytes per lane and chunk) ride in ONE register buffer: the next chunk's loads are
@@ -404,7 +406,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
             for (int i = 0; i < 8; ++i) {
               const float o0 = gelu_erf(v[c][4 * i + 1]) * v[c][4 * i];
               const float o1 = gelu_erf(v[c][4 * i + 3]) * v[c][4 * i + 2];
-              split2(o0, o1, hi[i], lo[i]);
+              if (g.u_scale > 0.f) split2u(o0 * g.u_scale, o1 * g.u_scale, hi[i], lo[i]);
+              else split2(o0, o1, hi[i], lo[i]);
             }
             if (row_ok) {
               const size_t off = (size_t)prow * g.ldu + (n >> 1);
@@ -525,7 +528,7 @@ int g_f16_bn = 0;   // omt_set_option("f16_bn", 0|128|256): tile N of the two-ac
 // A planes: [M, lda] fp16; W planes: [n_pad, K] fp16 (rows padded to 256); C fp32 (plain / QKV) or U planes (GEGLU)
 int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   using namespace f16g;
-  const bool rs = a.a_rs != nullptr;                  // row-scaled planes: one accumulator, 256-wide double-buffered tiles
+  const bool rs = a.a_rs != nullptr || a.a_rs_uniform > 0.f;   // row-scaled planes: one accumulator, 256-wide double-buffered tiles
   // two accumulators: 256-wide tiles hold ONE TMEM buffer (the drain is exposed: 1/3 of a K = 512 main loop), 128-wide
   // tiles two (but read A from L2 once per 128 columns) -- measured on B200: 128 wins only for the K = N = 512 shapes
   int BN = rs ? 256 : (g_f16_bn != 0 ? g_f16_bn : ((a.K <= 512 && a.N <= 512) ? 128 : 256));
@@ -572,6 +575,7 @@ int launch_gemm_f16(const omt_linear_h_args& a, cudaStream_t st) {
   g.n_split = dual ? a.n_split : 0x7fffffff;
   g.a_seg = a.a_seg; g.a_seg_stride = a.a_seg_stride; g.a_seg_off = a.a_seg_off;
   g.a_rs = a.a_rs; g.a2_rs = dual ? a.a2_rs : a.a_rs; g.w_scale = a.w_scale;
+  g.a_rs_uniform = a.a_rs_uniform; g.u_scale = a.u_scale;
   g.c_seg = a.c_seg; g.c_seg_stride = a.c_seg_stride; g.c_seg_off = a.c_seg_off;
   g.bias = a.bias; g.residual = a.residual; g.ldr = a.ldr;
   g.u_hi = a.u_hi; g.u_lo = a.u_lo; g.ldu = a.ldu;
@@ -596,7 +600,9 @@ extern "C" int omt_linear_h(const omt_linear_h_args* a, omt_stream_t stream) {
   OMT_REQUIRE(a->a_hi && a->a_lo && a->w_hi && a->w_lo, "omt_linear_h: null operand plane");
   OMT_REQUIRE((a->a2_hi == nullptr) == (a->a2_lo == nullptr), "omt_linear_h: the second A needs both planes");
   OMT_REQUIRE(a->a2_hi == nullptr || ((a->a_rs == nullptr) == (a->a2_rs == nullptr)), "omt_linear_h: both A operands must use the same plane format");
-  OMT_REQUIRE(a->a_rs == nullptr || (a->w_scale > 0.f && a->w_scale < 3.0e38f), "omt_linear_h: row-scaled planes need the weight scale");
+  OMT_REQUIRE((a->a_rs == nullptr && !(a->a_rs_uniform > 0.f)) || (a->w_scale > 0.f && a->w_scale < 3.0e38f), "omt_linear_h: row-scaled planes need the weight scale");
+  OMT_REQUIRE(a->a_rs == nullptr || !(a->a_rs_uniform > 0.f), "omt_linear_h: per-row and uniform A scales are exclusive");
+  OMT_REQUIRE(!(a->a_rs_uniform > 0.f) || a->a2_hi == nullptr, "omt_linear_h: the uniform A scale has no dual-A form");
   OMT_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "omt_linear_h: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   OMT_REQUIRE(a->epilogue == OMT_EPI_NONE || a->epilogue == OMT_EPI_GEGLU || a->epilogue == OMT_EPI_QKV || a->epilogue == OMT_EPI_QKV_PLANES,
               "omt_linear_h: unknown epilogue %d", a->epilogue);

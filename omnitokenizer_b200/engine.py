@@ -12,6 +12,7 @@ attention and both PEG variants go through index maps.
 """
 from __future__ import annotations
 
+import math
 import os
 from typing import Dict, Optional, Tuple
 
@@ -133,6 +134,8 @@ class Engine:
         self.planes = self.math == _cabi.MATH_F16X3
         # spatial attention core on fp16 operand planes (attention_f16.cu); 0 = the 3xTF32 core on the fp32 QKV buffer
         self.attn_f16 = self.planes and os.environ.get("OMT_ATTN_F16", "0") == "1"
+        # GEGLU output planes with a static (pack-time) scale -> the second FF GEMM takes the single-accumulator form
+        self.static_u = self.planes and os.environ.get("OMT_STATIC_U", "0") == "1"
         if a.attn_dropout != 0 or a.ff_dropout != 0:
             raise NotImplementedError("non-zero dropout reaches SDPA even in eval in the reference (attention.py:451); rejected")
         self._ws: Dict[Tuple, Workspace] = {}
@@ -182,7 +185,13 @@ class Engine:
         def ff(d, fp):
             d["ff_g"], d["ff_b"] = f32(sd[fp + ".0.weight"]), f32(sd[fp + ".0.bias"])
             d["ff1"] = PL(sd[fp + ".1.weight"], None, geglu=(self.inner, self.ku), row_scaled=True)
-            d["ff2"] = PL(sd[fp + ".4.weight"], None, k_pad=self.ku)
+            # |U| = |gelu(g) a| <= |g| |a| <= (|LN(x)|_2 max_n |W1_n|_2)^2 with |LN(x)|_2 <= max|gamma| sqrt(C) + |beta|_2: a bound
+            # known at pack time, so the U planes take ONE static power-of-two scale (single-accumulator FF2, no overflow possible)
+            w1 = sd[fp + ".1.weight"].detach().float()
+            ln_bound = float(d["ff_g"].abs().max()) * math.sqrt(self.C) + float(d["ff_b"].norm())
+            u_bound = (ln_bound * float(w1[:self.inner].norm(dim=1).max())) * (ln_bound * float(w1[self.inner:].norm(dim=1).max()))
+            d["u_scale"] = L.pow2_scale(u_bound) if self.static_u else 0.0
+            d["ff2"] = PL(sd[fp + ".4.weight"], None, k_pad=self.ku, row_scaled=self.static_u)
 
         def transformer(pre, block):
             layers = []
@@ -276,15 +285,19 @@ class Engine:
 
     def _linear_h(self, A: Planes, lin: PackedLinear, M, *, C=None, ldc=0, U: Optional[Planes] = None, A2: Optional[Planes] = None,
                   n_split=0, a_map=(0, 0, 0), c_map=(0, 0, 0), residual=None, ldr=0, epi=_cabi.EPI_NONE, qk=None,
-                  planes=None):
+                  planes=None, a_uniform=0.0, u_scale=0.0):
         """nn.Linear on operand planes (tcgen05 f16x3).  U: GEGLU output planes; qk: (q_scale, k_scale, cos, sin, qk_cols, tokens)."""
-        if (A.rs is not None) != lin.row_scaled:
+        if ((A.rs is not None) or a_uniform > 0.0) != lin.row_scaled:
             raise RuntimeError("operand planes and weight planes are in different f16x3 forms (row-scaled vs 2^11-scaled lo)")
         kw = dict(a_hi=A.hi, a_lo=A.lo, lda=A.ld, a_seg=a_map[0], a_seg_stride=a_map[1], a_seg_off=a_map[2],
                   w_hi=lin.w, w_lo=lin.w_lo, c=C, ldc=ldc, c_seg=c_map[0], c_seg_stride=c_map[1], c_seg_off=c_map[2],
                   M=M, N=lin.n, K=lin.k, bias=lin.bias, residual=residual, ldr=ldr, epilogue=epi)
         if A.rs is not None:
             kw.update(a_rs=A.rs, w_scale=lin.w_scale)
+        elif a_uniform > 0.0:
+            kw.update(a_rs_uniform=a_uniform, w_scale=lin.w_scale)
+        if u_scale > 0.0:
+            kw.update(u_scale=u_scale)
         if A2 is not None:
             kw.update(a2_hi=A2.hi, a2_lo=A2.lo, a2_rs=A2.rs, n_split=n_split)
         if U is not None:
@@ -369,8 +382,9 @@ class Engine:
             if H:
                 self._linear_h(ws.Op, proj, M, C=ws.X, ldc=C, residual=ws.X, ldr=C)
                 self._ln_h(ws.X, ws.XNp, lyr["ff_g"], lyr["ff_b"], M)
-                self._linear_h(ws.XNp, lyr["ff1"], M, U=ws.Up, epi=_cabi.EPI_GEGLU)
-                self._linear_h(ws.Up, lyr["ff2"], M, C=ws.X, ldc=C, residual=ws.X, ldr=C)
+                us = lyr["u_scale"]
+                self._linear_h(ws.XNp, lyr["ff1"], M, U=ws.Up, epi=_cabi.EPI_GEGLU, u_scale=us)
+                self._linear_h(ws.Up, lyr["ff2"], M, C=ws.X, ldc=C, residual=ws.X, ldr=C, a_uniform=(1.0 / us if us > 0 else 0.0))
             else:
                 self._linear(ws.O, C, proj, ws.X, C, M, residual=ws.X, ldr=C)
                 self._ln(ws.X, ws.XN, lyr["ff_g"], lyr["ff_b"], M)

@@ -280,6 +280,18 @@ def test_linear_h_row_scaled_epilogues(cuda):
                   M=M, N=2 * ku, K=K, epilogue=cabi.EPI_GEGLU)
     got = _join(U[0], U[1])
     assert (got[:, :inner] - ref).abs().max().item() < 4e-5 and torch.count_nonzero(U[:, :, inner:]).item() == 0
+    # statically scaled U planes (unscaled lo) feeding the second FF GEMM in the single-accumulator form
+    us = L.pow2_scale(float(ref.abs().max()) * 4.0)
+    cabi.linear_h(a_hi=ah, a_lo=al, a_rs=ars, w_scale=wsc, lda=K, w_hi=wh.to(cuda), w_lo=wl.to(cuda), u_hi=U[0], u_lo=U[1], ldu=ku,
+                  M=M, N=2 * ku, K=K, epilogue=cabi.EPI_GEGLU, u_scale=us)
+    got = (U[0].cpu().view(torch.float16).float() + U[1].cpu().view(torch.float16).float()) / us
+    assert (got[:, :inner] - ref).abs().max().item() < 4e-5
+    W2 = _rand((512, inner), 16, 0.05)
+    w2h, w2l, w2s = L.split_f16_rs(L.pad_rows(L.pad_cols(W2, ku), 256))
+    X = torch.empty(M, 512, device=cuda)
+    cabi.linear_h(a_hi=U[0], a_lo=U[1], a_rs_uniform=1.0 / us, w_scale=w2s, lda=ku, w_hi=w2h.to(cuda), w_lo=w2l.to(cuda), c=X, ldc=512,
+                  M=M, N=512, K=ku, epilogue=cabi.EPI_NONE)
+    assert (X.cpu() - (ref.double() @ W2.double().t()).float()).abs().max().item() < 4e-5
     # dual-A + rope / l2norm / scale
     Mq, N = 640, 128
     A1, A2, Wt = _rand((Mq, K), 70, 0.3), _rand((Mq, K), 71, 40.0), _rand((1536, K), 72, 0.05)

@@ -18,10 +18,16 @@ def _math_modes():
     return [m for m in os.environ.get("OMT_TEST_MATH", "fp32,3xtf32,f16x3").split(",") if m]
 
 
-@pytest.fixture(autouse=True, params=[m for m in os.environ.get("OMT_TEST_ATTN_F16", "0,1").split(",") if m])
-def _attention_core(request, monkeypatch):
-    """every model-level test runs with the 3xTF32 attention core and with the fp16-plane core (f16x3 math only uses it)"""
-    monkeypatch.setenv("OMT_ATTN_F16", request.param)
+VARIANTS = {"base": dict(OMT_ATTN_F16="0", OMT_STATIC_U="0", OMT_PEG_KERNEL="3"),
+            # fp16-plane attention core, statically scaled GEGLU planes (single-accumulator FF2), persistent PEG
+            "fast": dict(OMT_ATTN_F16="1", OMT_STATIC_U="1", OMT_PEG_KERNEL="5")}
+
+
+@pytest.fixture(autouse=True, params=[v for v in os.environ.get("OMT_TEST_VARIANTS", "base,fast").split(",") if v])
+def _kernel_variant(request, monkeypatch):
+    """every model-level test runs with the conservative kernel set and with the fast one (the latter only differs in f16x3 math)"""
+    for k, v in VARIANTS[request.param].items():
+        monkeypatch.setenv(k, v)
     yield
 
 
