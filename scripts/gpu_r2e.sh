@@ -9,7 +9,7 @@ TMO=600 run ops python -m pytest tests/test_gpu_ops.py tests/test_gpu_f16x3.py t
 TMO=300 run ops_qkvplanes python -m pytest tests/test_gpu_f16x3.py -x -q -k "qkv_planes"
 TMO=300 run ops_attn_h python -m pytest tests/test_gpu_f16x3.py -x -q -k "attn_spatial_h"
 TMO=900 OMT_TEST_VARIANTS=base run model python -m pytest tests/test_gpu_model.py -x -q
-TMO=600 OMT_TEST_VARIANTS=fast OMT_TEST_MATH=f16x3 OMT_ATTN_F16=0 run model_u_peg python -m pytest tests/test_gpu_model.py -x -q -s -k "golden"
+TMO=600 OMT_TEST_VARIANTS=upeg OMT_TEST_MATH=f16x3 run model_u_peg python -m pytest tests/test_gpu_model.py -x -q -s -k "golden"
 TMO=900 OMT_TEST_VARIANTS=fast OMT_TEST_MATH=f16x3 run model_fast python -m pytest tests/test_gpu_model.py -x -q -s
 TMO=600 run bench_cfg3 python bench.py --steps 20 --warmup 5
 TMO=400 OMT_STATIC_U=1 run bench_cfg3_u python bench.py --steps 10 --warmup 3 --no-cpu-baseline

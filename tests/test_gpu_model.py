@@ -20,7 +20,8 @@ def _math_modes():
 
 VARIANTS = {"base": dict(OMT_ATTN_F16="0", OMT_STATIC_U="0", OMT_PEG_KERNEL="3"),
             # fp16-plane attention core, statically scaled GEGLU planes (single-accumulator FF2), persistent PEG
-            "fast": dict(OMT_ATTN_F16="1", OMT_STATIC_U="1", OMT_PEG_KERNEL="5")}
+            "fast": dict(OMT_ATTN_F16="1", OMT_STATIC_U="1", OMT_PEG_KERNEL="5"),
+            "upeg": dict(OMT_ATTN_F16="0", OMT_STATIC_U="1", OMT_PEG_KERNEL="5")}      # bring-up: fast minus the attention core
 
 
 @pytest.fixture(autouse=True, params=[v for v in os.environ.get("OMT_TEST_VARIANTS", "base,fast").split(",") if v])
