@@ -129,10 +129,12 @@ def cpu_oracle_run(sd, x, reps=1, vae=False):
     return best, idx, rec
 
 
-def near_tie_report(sd, x, idx_o, idx_g):
-    """For code indices that differ from the oracle's: the float64 distance gap between the two codes at the oracle's own
-    pre-quantisation vector.  A gap below fp32 resolution of the distance (d is O(1), ulp 1.2e-7) is a tie the oracle's own
-    fp32 summation order decides, not an error of the GPU path."""
+def near_tie_report(sd, x, idx_o, idx_g, z_gpu):
+    """Explain every code index that differs from the oracle's.  Both sides compute the pre-quantisation vector z in fp32
+    with different summation orders (|z_gpu - z_oracle| ~ 1e-6 after 12 layers); a change dz moves the distance gap
+    between two codes e_a, e_b by 2 dz.(e_b - e_a).  An index may therefore differ only where the float64 gap at the
+    oracle's z is no larger than that bound (+ a few fp32 ulps of the O(1) distances): a tie at fp32 resolution of z,
+    which the reference's own GPU and CPU runs would break differently as well."""
     from oracle import omni_oracle as oo
     cfg = oo.Config()
     oo.USE_LIBRARY_OPS = True
@@ -141,10 +143,17 @@ def near_tie_report(sd, x, idx_o, idx_g):
     z = h.reshape(-1, h.shape[-1]).double()
     z = z / z.norm(dim=1, keepdim=True).clamp_min(1e-12)
     E = sd["codebook.embeddings"].double()
-    bad = (idx_g.reshape(-1) != idx_o.reshape(-1)).nonzero().flatten()
-    gaps = [float(((z[i] - E[idx_g.reshape(-1)[i]]) ** 2).sum() - ((z[i] - E[idx_o.reshape(-1)[i]]) ** 2).sum()) for i in bad]
-    return {"rows": bad.tolist()[:8], "f64_distance_gap": [float(f"{g:.3e}") for g in gaps[:8]],
-            "all_within_fp32_ulp_of_d": bool(all(abs(g) < 2.4e-7 for g in gaps))}
+    ig, io = idx_g.reshape(-1), idx_o.reshape(-1)
+    bad = (ig != io).nonzero().flatten()
+    rep = []
+    for i in bad.tolist():
+        gap = float(((z[i] - E[ig[i]]) ** 2).sum() - ((z[i] - E[io[i]]) ** 2).sum())
+        dz = z_gpu[i].double().cpu() - z[i]
+        bound = float(2.0 * dz.norm() * (E[ig[i]] - E[io[i]]).norm()) + 4 * 1.2e-7
+        rep.append({"row": i, "f64_distance_gap": float(f"{gap:.3e}"), "abs_dz": float(f"{float(dz.abs().max()):.3e}"),
+                    "tie_bound": float(f"{bound:.3e}"), "within_bound": bool(abs(gap) <= bound)})
+    return {"rows": rep[:8], "all_within_fp32_resolution_of_z": bool(all(r["within_bound"] for r in rep)),
+            "max_abs_dz_all_rows": float(f"{float((z_gpu.double().cpu() - z).abs().max()):.3e}")}
 
 
 def _ref_worker(threads, sd, vae, q_in, q_out):
@@ -519,7 +528,9 @@ def main():
                 line["parity"] = {"idx_mismatch": mism, "n_idx": idx_o.numel(),
                                   "max_abs_pixel_err": float((rec_g.cpu() - rec_o).abs().max())}
                 if mism:     # explain every differing index, and compare the decoder on the oracle's own indices
-                    line["parity"]["near_tie"] = near_tie_report(sd, xs, idx_o, idx_g.cpu())
+                    eng = m.engine()
+                    z_gpu = eng.z_view(eng._workspace(idx_o.numel())).clone()       # z of the encode() just above
+                    line["parity"]["near_tie"] = near_tie_report(sd, xs, idx_o, idx_g.cpu(), z_gpu)
                     line["parity"]["max_abs_pixel_err_same_codes"] = float(
                         (m.decode(idx_o.to(dev), is_image).cpu() - rec_o).abs().max())
         print(json.dumps(line))

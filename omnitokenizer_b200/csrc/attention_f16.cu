@@ -32,7 +32,7 @@ constexpr int TILE = KT * D * 2;                    // 8 KiB: one 64 x 64 fp16 p
 constexpr int STAGE_BYTES = 4 * TILE + 1024;        // K_hi, K_lo, V_hi, V_lo + vinv (256 B, padded to keep 1024-B alignment)
 constexpr int STAGES = 4;
 constexpr int OFF_CTRL = STAGES * STAGE_BYTES;
-constexpr int SMEM = OFF_CTRL + 2048 + 1024;        // barriers / exchange + alignment slack
+constexpr int SMEM = OFF_CTRL + 3072 + 1024;        // barriers / exchange + alignment slack
 constexpr int TM_S = 0, TM_O = 128, TM_P = 256, TM_Q = 384;
 constexpr int THREADS = 64 + 256;                   // TMA, MMA, 8 softmax warps
 constexpr uint32_t IDESC_S = idesc_f16(128, 64, false, false);                      // A: TMEM, B: K-major smem
@@ -83,8 +83,8 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
   uint64_t* p_full = bars + 16;
   uint64_t& q_ready = bars[18];
   uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 20);
-  float* xch = reinterpret_cast<float*>(smem + OFF_CTRL + 256);        // [2 key halves][128 rows] row-max / row-sum exchange
-  float* red = reinterpret_cast<float*>(smem + OFF_CTRL + 256 + 1024); // [8] per-warp maxima of vinv
+  float* xch = reinterpret_cast<float*>(smem + OFF_CTRL + 256);        // [2 tile parities][2 key halves][128 rows] row-max / row-sum exchange
+  float* red = reinterpret_cast<float*>(smem + OFF_CTRL + 256 + 2048); // [8] per-warp maxima of vinv
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
@@ -240,28 +240,35 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
       float mx = sv[0];
 #pragma unroll
       for (int i = 1; i < 32; ++i) mx = fmaxf(mx, sv[i]);
-      xch[half * QT + r] = mx;
+      // the slot alternates with the tile parity: the partner passes the NEXT tile's barrier only after this read, and
+      // that barrier comes before anyone writes this slot again -- one barrier per tile is enough
+      xch[(b * 2 + half) * QT + r] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(mx, xch[(half ^ 1) * QT + r]);
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");   // partner has read before the slot is reused
+      mx = fmaxf(mx, xch[(b * 2 + (half ^ 1)) * QT + r]);
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * a.scale_log2);
-      float psum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { sv[i] = exp2f((sv[i] - m_new) * a.scale_log2); psum += sv[i]; }
-      l_run = l_run * alpha + psum;                  // partial row sum over this thread's keys
-      m_run = m_new;
-      // P'' = p * vinv_j * 2^ep as fp16 hi / lo (unscaled), two keys per 32-bit TMEM column; the K / V tile's full
-      // barrier (waited on by the MMA warp before S(j)) already covers the vinv slice this thread reads
+      const float alpha = ex2_fast((m_run - m_new) * a.scale_log2);
+      // p = 2^((s - m) * c) on packed key pairs, P'' = p * (vinv_j * 2^ep) as unscaled fp16 hi / lo planes, two
+      // keys per 32-bit TMEM column.  The K / V tile's full barrier (waited on above) covers the vinv slice.
       {
+        const float2 c2 = make_float2(a.scale_log2, a.scale_log2);
+        const float2 nm2 = make_float2(-m_new, -m_new);
+        const float2 ps2 = make_float2(p_scale, p_scale);
         const float4* vi = reinterpret_cast<const float4*>(smem + (size_t)s * STAGE_BYTES + 4 * TILE) + half * 8;
+        float2 ps = make_float2(0.f, 0.f);
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 w = vi[i];
-          split2u(sv[4 * i] * (w.x * p_scale), sv[4 * i + 1] * (w.y * p_scale), hi[2 * i], lo[2 * i]);
-          split2u(sv[4 * i + 2] * (w.z * p_scale), sv[4 * i + 3] * (w.w * p_scale), hi[2 * i + 1], lo[2 * i + 1]);
+          float2 e0 = fmul2(fadd2(make_float2(sv[4 * i], sv[4 * i + 1]), nm2), c2);       // (s - m) * c: the row maximum maps to exactly 0
+          float2 e1 = fmul2(fadd2(make_float2(sv[4 * i + 2], sv[4 * i + 3]), nm2), c2);
+          e0.x = ex2_fast(e0.x); e0.y = ex2_fast(e0.y);
+          e1.x = ex2_fast(e1.x); e1.y = ex2_fast(e1.y);
+          ps = fadd2(ps, fadd2(e0, e1));
+          split2u_pk(fmul2(e0, fmul2(make_float2(w.x, w.y), ps2)), hi[2 * i], lo[2 * i]);
+          split2u_pk(fmul2(e1, fmul2(make_float2(w.z, w.w), ps2)), hi[2 * i + 1], lo[2 * i + 1]);
         }
+        l_run = fmaf(l_run, alpha, ps.x + ps.y);     // partial row sum over this thread's keys
+        m_run = m_new;
         const uint32_t pbase = tmem_base + lane_addr + TM_P + b * 64 + half * 16;
         tmem_st16(pbase, hi);
         tmem_st16(pbase + 32, lo);
@@ -276,8 +283,12 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
         tc_fence_after();
         float oj[32];
         tmem_ld32(tmem_base + TM_O + lane_addr + (jp & 1) * 64 + half * 32, oj);
+        const float2 al2 = make_float2(alpha_prev, alpha_prev);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha_prev, oj[i]);
+        for (int i = 0; i < 32; i += 2) {
+          const float2 t = ffma2(make_float2(o_acc[i], o_acc[i + 1]), al2, make_float2(oj[i], oj[i + 1]));
+          o_acc[i] = t.x; o_acc[i + 1] = t.y;
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[jp & 1]);
@@ -295,9 +306,10 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
       tc_fence_before();
     }
     // total row sum = the two partial sums (same running max on both sides); 2^-ep undoes the P'' scale
-    xch[half * QT + r] = l_run;
+    const int fb = ntiles & 1;                       // the parity the last tile did not use
+    xch[(fb * 2 + half) * QT + r] = l_run;
     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-    const float inv = p_inv / (l_run + xch[(half ^ 1) * QT + r]);
+    const float inv = p_inv / (l_run + xch[(fb * 2 + (half ^ 1)) * QT + r]);
     const size_t ooff = (size_t)(row_q0 + r) * a.ldo + col0 + half * 32;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {

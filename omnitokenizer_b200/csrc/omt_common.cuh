@@ -135,6 +135,36 @@ __device__ __forceinline__ void store_split4u(uint16_t* hi, uint16_t* lo, size_t
   *reinterpret_cast<uint2*>(hi + off) = h;
   *reinterpret_cast<uint2*>(lo + off) = l;
 }
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): one issue slot for two lanes of work, each half rounds like the scalar op
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<uint64_t*>(&d))
+      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)), "l"(*reinterpret_cast<const uint64_t*>(&c)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t*>(&d))
+      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t*>(&d))
+      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+  return d;
+}
+__device__ __forceinline__ float ex2_fast(float x) {      // MUFU.EX2 alone; results below 2^-126 flush to zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// unscaled hi / lo planes of a pair (the pair already carries its row scale)
+__device__ __forceinline__ void split2u_pk(float2 v, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = pack_f16x2_sat(v.x, v.y);
+  const float2 d = ffma2(unpack_f16x2(hi2), make_float2(-1.f, -1.f), v);      // v - hi, exact
+  lo2 = pack_f16x2_sat(d.x, d.y);
+}
 __device__ __forceinline__ float max4abs(float4 v) { return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))); }
 
 __device__ __forceinline__ float gelu_erf(float x) {

@@ -460,15 +460,6 @@ __global__ void __launch_bounds__(256) peg_tile_kernel(const float* __restrict__
 //   * packed fma.rn.f32x2 (FFMA2): one instruction per channel PAIR and tap.
 // Requires T <= 64, w <= 254 (multiply-shift range) and 16-byte aligned x; the host falls back to v3 otherwise.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(*reinterpret_cast<uint64_t*>(&d))
-      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)),
-        "l"(*reinterpret_cast<const uint64_t*>(&c)));
-  return d;
-}
-
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));

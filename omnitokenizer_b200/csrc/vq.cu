@@ -74,14 +74,6 @@ constexpr int VQF_ROWS = 512;                 // rows per cluster
 constexpr int VQF_THREADS = 128;              // 4 rows per thread
 constexpr int VQF_OWN = VQF_ROWS / VQF_SLICES;   // rows projected / finalised per CTA
 
-__device__ __forceinline__ float2 vq_ffma2(const float2 a, const float2 b, const float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(*reinterpret_cast<uint64_t*>(&d))
-      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)),
-        "l"(*reinterpret_cast<const uint64_t*>(&c)));
-  return d;
-}
 __device__ __forceinline__ uint32_t vq_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t vq_mapa(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -203,7 +195,7 @@ vq_fused_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
     for (int p = 0; p < 2; ++p) {
       float2 dot = make_float2(zp[p][0].x * ev[0], zp[p][0].y * ev[0]);
 #pragma unroll
-      for (int j = 1; j < 8; ++j) dot = vq_ffma2(zp[p][j], make_float2(ev[j], ev[j]), dot);
+      for (int j = 1; j < 8; ++j) dot = ffma2(zp[p][j], make_float2(ev[j], ev[j]), dot);
       const float d0 = (zz[2 * p] - dot.x) + ek, d1 = (zz[2 * p + 1] - dot.y) + ek;
       if (d0 < best[2 * p]) { best[2 * p] = d0; bi[2 * p] = k; }             // strict <  => first minimum wins
       if (d1 < best[2 * p + 1]) { best[2 * p + 1] = d1; bi[2 * p + 1] = k; }

@@ -132,8 +132,8 @@ class Engine:
             raise NotImplementedError(f"--codebook_dim {self.cd}: the VQ search / post_vq kernels are specialised for "
                                       "codebook_dim 8 (every shipped config); VAE mode takes 8 latent channels as well")
         self.planes = self.math == _cabi.MATH_F16X3
-        # spatial attention core on fp16 operand planes (attention_f16.cu); 0 = the 3xTF32 core on the fp32 QKV buffer
-        self.attn_f16 = self.planes and os.environ.get("OMT_ATTN_F16", "0") == "1"
+        # spatial attention core on fp16 operand planes (attention_f16.cu, default); OMT_ATTN_F16=0 = the 3xTF32 core on the fp32 QKV buffer
+        self.attn_f16 = self.planes and os.environ.get("OMT_ATTN_F16", "1") == "1"
         # GEGLU output planes with a static (pack-time) scale -> the second FF GEMM takes the single-accumulator form
         self.static_u = self.planes and os.environ.get("OMT_STATIC_U", "0") == "1"
         if a.attn_dropout != 0 or a.ff_dropout != 0:
