@@ -15,10 +15,10 @@
 //     canonical SWIZZLE_128B MN-major layout, so nothing is transposed anywhere.
 //   * the per-key inverse V scale is folded into P: P'' = p * vinv_j * 2^ep with ONE power of two per CTA taken from the
 //     largest vinv of the sequence, so p'' stays in fp16 range; 2^-ep comes off with the final 1 / row-sum.
-//   TMEM columns: S[2] 0-127 | O[2] 128-255 | P[2] x (hi 32 | lo 32) 256-383 | Q (hi 32 | lo 32) 384-447
+//   TMEM columns: S[2] 0-127 | O 128-191 (accumulates over the key tiles) | P[2] x (hi 32 | lo 32) 256-383 | Q (hi 32 | lo 32) 384-447
 //   smem stage  : K_hi | K_lo | V_hi | V_lo (8 KiB each) | vinv (256 B), 4 stages, every tile one TMA transaction set
 // Roles: warp 0 TMA, warp 1 MMA issue + TMEM alloc, warps 2-9 softmax: TWO threads per query row (32 keys / 32 output
-//        dims each; they only exchange the row max), S from TMEM, P back to TMEM, O accumulated in registers.
+//        dims each; they only exchange the row max), S from TMEM, P back to TMEM, O read back once at the end.
 #include "omt_common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
@@ -79,7 +79,7 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
   uint64_t* full = bars;            // [STAGES] K / V planes + vinv of a key tile landed
   uint64_t* empty = bars + 4;       // [STAGES] P.V of the tile retired (commit) and the 8 softmax warps are done with vinv
   uint64_t* s_full = bars + 8;  uint64_t* s_empty = bars + 10;
-  uint64_t* o_full = bars + 12; uint64_t* o_empty = bars + 14;
+  uint64_t* o_full = bars + 12;     // [2] P.V of a tile retired (per P buffer)
   uint64_t* p_full = bars + 16;
   uint64_t& q_ready = bars[18];
   uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 20);
@@ -101,7 +101,7 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + 8); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8);
+      mbar_init(&o_full[i], 1);
       mbar_init(&p_full[i], 8);
     }
     mbar_init(&q_ready, 8);
@@ -165,16 +165,15 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
       const int s = j % STAGES, b = j & 1;
       const uint32_t ph2 = (j >> 1) & 1;
       mbar_wait(&p_full[b], ph2);
-      mbar_wait(&o_empty[b], ph2 ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d = tmem_base + TM_O + b * 64;
+        const uint32_t d = tmem_base + TM_O;         // O accumulates in place over the key tiles (the softmax threads rescale it)
         const uint32_t p_hi = tmem_base + TM_P + b * 64, p_lo = p_hi + 32;
         const uint32_t vh = sb + s * STAGE_BYTES + 2 * TILE, vl = vh + TILE;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {           // 16 keys per MMA: 16 rows of the MN-major V tile = 2 KiB
           const uint64_t dvh = desc_mnmajor(vh + kk * 2048), dvl = desc_mnmajor(vl + kk * 2048);
-          mma_f16_ts(d, p_lo + kk * 8, dvh, IDESC_PV, kk != 0);
+          mma_f16_ts(d, p_lo + kk * 8, dvh, IDESC_PV, (j | kk) != 0);
           mma_f16_ts(d, p_hi + kk * 8, dvl, IDESC_PV, 1);
           mma_f16_ts(d, p_hi + kk * 8, dvh, IDESC_PV, 1);
         }
@@ -223,10 +222,14 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
     float p_scale, p_inv;
     row_scale(vmx, p_scale, p_inv);                  // p * vinv_j * p_scale <= 2^15 for every key
 
-    float o_acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    // Lazy running maximum: the reference point m_used of a row only moves when a tile's maximum exceeds it by more than
+    // 2^TAU (in the exponent); until then p = 2^((s - m_used) c) <= 2^TAU, which the P'' scale leaves room for.  O therefore
+    // accumulates IN tensor memory across the key tiles (no per-tile read-back: TMEM reads run at 64 B/clk/SM and were half of
+    // the softmax threads' tile time); on the rare move the owning threads rescale their O rows in place.
+    constexpr float TAU = 8.f;
+    const float p_scale_l = p_scale * 0x1p-8f, p_inv_l = p_inv * 0x1p8f;
+    float m_used = -INFINITY, l_run = 0.f;
+    const uint32_t o_addr = tmem_base + TM_O + lane_addr + half * 32;
     for (int j = 0; j < ntiles; ++j) {
       const int b = j & 1, s = j % STAGES;
       float sv[32];
@@ -245,21 +248,36 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
       xch[(b * 2 + half) * QT + r] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       mx = fmaxf(mx, xch[(b * 2 + (half ^ 1)) * QT + r]);
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2_fast((m_run - m_new) * a.scale_log2);
-      // p = 2^((s - m) * c) on packed key pairs, P'' = p * (vinv_j * 2^ep) as unscaled fp16 hi / lo planes, two
+      const bool grow = (mx - m_used) * a.scale_log2 > TAU;          // always true on the first tile (m_used = -inf)
+      float alpha = 1.f;
+      if (grow) { alpha = ex2_fast((m_used - mx) * a.scale_log2); m_used = mx; }
+      if (j >= 2) mbar_wait(&o_full[b], ((j - 2) >> 1) & 1);         // P.V of tile j-2 no longer reads this P buffer
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        // rescale this warp's O rows in place: every P.V issued so far (tile j-1 is the last) must have retired, and P.V(j)
+        // is not issued before all eight warps have arrived on p_full below
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        float ov[32];
+        tmem_ld32(o_addr, ov);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ov[i] *= alpha;
+        tmem_st32(o_addr, ov);
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      // p = 2^((s - m_used) * c) on packed key pairs, P'' = p * (vinv_j * 2^ep) as unscaled fp16 hi / lo planes, two
       // keys per 32-bit TMEM column.  The K / V tile's full barrier (waited on above) covers the vinv slice.
       {
         const float2 c2 = make_float2(a.scale_log2, a.scale_log2);
-        const float2 nm2 = make_float2(-m_new, -m_new);
-        const float2 ps2 = make_float2(p_scale, p_scale);
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        const float2 ps2 = make_float2(p_scale_l, p_scale_l);
         const float4* vi = reinterpret_cast<const float4*>(smem + (size_t)s * STAGE_BYTES + 4 * TILE) + half * 8;
         float2 ps = make_float2(0.f, 0.f);
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 w = vi[i];
-          float2 e0 = fmul2(fadd2(make_float2(sv[4 * i], sv[4 * i + 1]), nm2), c2);       // (s - m) * c: the row maximum maps to exactly 0
+          float2 e0 = fmul2(fadd2(make_float2(sv[4 * i], sv[4 * i + 1]), nm2), c2);       // (s - m) * c: the reference point maps to exactly 0
           float2 e1 = fmul2(fadd2(make_float2(sv[4 * i + 2], sv[4 * i + 3]), nm2), c2);
           e0.x = ex2_fast(e0.x); e0.y = ex2_fast(e0.y);
           e1.x = ex2_fast(e1.x); e1.y = ex2_fast(e1.y);
@@ -268,7 +286,6 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
           split2u_pk(fmul2(e1, fmul2(make_float2(w.z, w.w), ps2)), hi[2 * i + 1], lo[2 * i + 1]);
         }
         l_run = fmaf(l_run, alpha, ps.x + ps.y);     // partial row sum over this thread's keys
-        m_run = m_new;
         const uint32_t pbase = tmem_base + lane_addr + TM_P + b * 64 + half * 16;
         tmem_st16(pbase, hi);
         tmem_st16(pbase + 32, lo);
@@ -277,39 +294,20 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&p_full[b]); mbar_arrive(&empty[s]); }
-      if (j > 0) {
-        const int jp = j - 1;
-        mbar_wait(&o_full[jp & 1], (jp >> 1) & 1);
-        tc_fence_after();
-        float oj[32];
-        tmem_ld32(tmem_base + TM_O + lane_addr + (jp & 1) * 64 + half * 32, oj);
-        const float2 al2 = make_float2(alpha_prev, alpha_prev);
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float2 t = ffma2(make_float2(o_acc[i], o_acc[i + 1]), al2, make_float2(oj[i], oj[i + 1]));
-          o_acc[i] = t.x; o_acc[i + 1] = t.y;
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[jp & 1]);
-      }
-      alpha_prev = alpha;
     }
+    float o_acc[32];
     {
       const int jp = ntiles - 1;
       mbar_wait(&o_full[jp & 1], (jp >> 1) & 1);
       tc_fence_after();
-      float oj[32];
-      tmem_ld32(tmem_base + TM_O + lane_addr + (jp & 1) * 64 + half * 32, oj);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha_prev, oj[i]);
+      tmem_ld32(o_addr, o_acc);
       tc_fence_before();
     }
     // total row sum = the two partial sums (same running max on both sides); 2^-ep undoes the P'' scale
     const int fb = ntiles & 1;                       // the parity the last tile did not use
     xch[(fb * 2 + half) * QT + r] = l_run;
     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-    const float inv = p_inv / (l_run + xch[(fb * 2 + (half ^ 1)) * QT + r]);
+    const float inv = p_inv_l / (l_run + xch[(fb * 2 + (half ^ 1)) * QT + r]);
     const size_t ooff = (size_t)(row_q0 + r) * a.ldo + col0 + half * 32;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {

@@ -56,23 +56,24 @@ __global__ void __launch_bounds__(256) pre_vq_kernel(const float* __restrict__ x
 // Fused VQ lookup: pre_vq projection + l2 normalise + || z ||^2 - 2 z E^T + || E ||^2 + argmin (+ usage histogram) in
 // ONE launch (modules/codebook.py:82-86 after omnitokenizer.py:248-252).
 //
-// A cluster of 8 CTAs owns a block of 512 rows; CTA r of the cluster
-//   A. projects rows [64 r, 64 r + 64) of the block (warp per row, the arithmetic of pre_vq_kernel) and broadcasts the
-//      8 floats of each z row into the z table of ALL 8 CTAs through distributed shared memory (and to global z);
-//   B. searches ALL 512 rows against ITS slice of the codebook (n_codes / 8 codes + their || E ||^2, staged once in
-//      shared memory with coalesced 16-byte reads): a thread owns 4 rows, so one broadcast read of a code (36 bytes)
-//      feeds 32 FMAs -- issued as 16 packed fma.rn.f32x2 over row pairs -- instead of 8 (the old kernel was
-//      shared-memory-bound at 0.27 of the FMA peak);
+// A cluster of 8 CTAs owns a block of 128 R rows (R = 4, or 2 for small inputs); CTA r of the cluster
+//   A. projects rows [16 R r, 16 R (r + 1)) of the block (warp per row, the arithmetic of pre_vq_kernel) and broadcasts
+//      the 8 floats of each z row into the z table of ALL 8 CTAs through distributed shared memory (and to global z);
+//   B. searches ALL rows of the block against ITS slice of the codebook (n_codes / 8 codes + their || E ||^2, staged
+//      once in shared memory with coalesced 16-byte reads): a thread keeps R rows of z in registers, so one broadcast
+//      read of a code (36 bytes) feeds 8 R FMAs.  The minimum is tracked per GROUP of 8 codes (one FMNMX per distance,
+//      one compare-and-select per group instead of per code -- the per-code compare / select pair was a third of the
+//      old kernel's instructions); the winning group is re-evaluated once at the end with the same instruction
+//      sequence, so the first code whose distance equals the group minimum bit for bit is the first minimum;
 //   C. sends its per-row (distance, index) to the CTA that owns the row (DSMEM again); the owner takes the first minimum
 //      over the 8 slices in ascending slice order == torch.argmin's first-min rule, writes the int64 index and bumps
 //      the histogram that replaces torch.unique (codebook.py:65).
-// Distances keep the reference association (sum z^2 - 2 z.E) + sum E^2 with the sequential fma chain of the old
-// kernel, so indices are bit-identical to it.  No workspace, no second launch.
+// Distances keep the reference association (sum z^2 - 2 z.E) + sum E^2 with a sequential fma chain over the 8 dims.
+// Shared memory: [slice 36 B / code | projection weights during A]  [z table, reused for the partial minima in C].
 // ---------------------------------------------------------------------------------------
 constexpr int VQF_SLICES = 8;                 // cluster size = codebook slices
-constexpr int VQF_ROWS = 512;                 // rows per cluster
-constexpr int VQF_THREADS = 128;              // 4 rows per thread
-constexpr int VQF_OWN = VQF_ROWS / VQF_SLICES;   // rows projected / finalised per CTA
+constexpr int VQF_THREADS = 128;
+constexpr int VQF_GROUP = 8;                  // codes per minimum group
 
 __device__ __forceinline__ uint32_t vq_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t vq_mapa(uint32_t addr, uint32_t rank) {
@@ -80,39 +81,47 @@ __device__ __forceinline__ uint32_t vq_mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void vq_cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+__device__ __forceinline__ void vq_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void vq_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// distance of one row (2 z in z2[], sum z^2 in zz) to one code: the exact instruction sequence both passes share
+__device__ __forceinline__ float vq_dist(const float (&z2)[8], float zz, const float4 ea, const float4 eb, float ek) {
+  float dot = __fmul_rn(z2[0], ea.x);
+  dot = fmaf(z2[1], ea.y, dot); dot = fmaf(z2[2], ea.z, dot); dot = fmaf(z2[3], ea.w, dot);
+  dot = fmaf(z2[4], eb.x, dot); dot = fmaf(z2[5], eb.y, dot); dot = fmaf(z2[6], eb.z, dot); dot = fmaf(z2[7], eb.w, dot);
+  return __fadd_rn(__fsub_rn(zz, dot), ek);
 }
 
-template <bool PROJECT>       // PROJECT: rows come from x . Wt^T + b (fused pre_vq); else z is given
+template <bool PROJECT, int R>       // PROJECT: rows come from x . Wt^T + b (fused pre_vq); else z is given.  R rows / thread
 __global__ void __cluster_dims__(VQF_SLICES, 1, 1) __launch_bounds__(VQF_THREADS)
 vq_fused_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ Wt, const float* __restrict__ bias, int C, int l2,
                 const float* __restrict__ z_in, float* __restrict__ z_out, const float* __restrict__ E,
                 const float* __restrict__ e2, int M, int n_codes, int64_t* __restrict__ idx, int32_t* __restrict__ counts) {
+  constexpr int ROWS = R * VQF_THREADS;        // rows per cluster
+  constexpr int OWN = ROWS / VQF_SLICES;       // rows projected / finalised per CTA
   pdl_sync();
   extern __shared__ __align__(16) uint8_t vq_smem[];
   const int per = n_codes / VQF_SLICES;
   float4* esm = reinterpret_cast<float4*>(vq_smem);                          // [per][2] float4: this slice of the table
   float* e2s = reinterpret_cast<float*>(esm + 2 * per);                      // [per]
-  float4* zsm = reinterpret_cast<float4*>(e2s + per);                        // [512][2] float4: the block's z rows
-  float2* part = reinterpret_cast<float2*>(zsm + 2 * VQF_ROWS);              // [8 slices][64 own rows] (distance, index bits)
-  float4* wsm = reinterpret_cast<float4*>(part + VQF_SLICES * VQF_OWN);      // PROJECT: [8][C/4] projection weights
+  float4* wsm = reinterpret_cast<float4*>(vq_smem);                          // PROJECT, phase A only: [8][C/4] weights
+  float4* zsm = reinterpret_cast<float4*>(vq_smem + (size_t)per * 36);       // [ROWS][2] float4: the block's z rows
+  float2* part = reinterpret_cast<float2*>(zsm);                             // phase C: [8 slices][OWN] (distance, index bits)
   const uint32_t rank = vq_cluster_rank();
-  const int row0 = (blockIdx.x / VQF_SLICES) * VQF_ROWS;
+  const int row0 = (blockIdx.x / VQF_SLICES) * ROWS;
   const int k0 = (int)rank * per;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  vq_cluster_arrive();          // no CTA touches a peer's shared memory before every CTA of the cluster is running
 
-  for (int i = tid; i < 2 * per; i += VQF_THREADS) esm[i] = reinterpret_cast<const float4*>(E + (size_t)k0 * 8)[i];
-  for (int i = tid; i < per; i += VQF_THREADS) e2s[i] = e2[k0 + i];
-  // ---- A. this CTA's 64 rows of z -> the z table of every CTA of the cluster
+  // ---- A. this CTA's OWN rows of z -> the z table of every CTA of the cluster
   const uint32_t zsm_s = static_cast<uint32_t>(__cvta_generic_to_shared(zsm));
   if (PROJECT) {
     const int C4 = C >> 2;
     for (int i = tid; i < 8 * C4; i += VQF_THREADS) wsm[i] = reinterpret_cast<const float4*>(Wt)[i];
     __syncthreads();
-    for (int rr = warp; rr < VQF_OWN; rr += VQF_THREADS / 32) {
-      const int lrow = (int)rank * VQF_OWN + rr, row = row0 + lrow;
+    vq_cluster_wait();
+    for (int rr = warp; rr < OWN; rr += VQF_THREADS / 32) {
+      const int lrow = (int)rank * OWN + rr, row = row0 + lrow;
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -155,8 +164,9 @@ vq_fused_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
       }
     }
   } else {
-    for (int i = tid; i < VQF_OWN * 2; i += VQF_THREADS) {          // this CTA's 64 rows, 2 float4 each
-      const int lrow = (int)rank * VQF_OWN + (i >> 1), row = row0 + lrow;
+    vq_cluster_wait();
+    for (int i = tid; i < OWN * 2; i += VQF_THREADS) {              // this CTA's rows, 2 float4 each
+      const int lrow = (int)rank * OWN + (i >> 1), row = row0 + lrow;
       const float4 v = row < M ? reinterpret_cast<const float4*>(z_in + (size_t)row * 8)[i & 1] : make_float4(0.f, 0.f, 0.f, 0.f);
       for (uint32_t r = 0; r < VQF_SLICES; ++r) {
         const uint32_t dst = vq_mapa(zsm_s + (uint32_t)lrow * 32u + (uint32_t)(i & 1) * 16u, r);
@@ -164,60 +174,78 @@ vq_fused_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
       }
     }
   }
-  vq_cluster_sync();            // every CTA holds all 512 z rows (and its own table slice: __syncthreads is implied)
+  vq_cluster_arrive();          // every CTA holds all z rows after this barrier; this CTA is also done with wsm
+  vq_cluster_wait();
+  for (int i = tid; i < 2 * per; i += VQF_THREADS) esm[i] = reinterpret_cast<const float4*>(E + (size_t)k0 * 8)[i];
+  for (int i = tid; i < per; i += VQF_THREADS) e2s[i] = e2[k0 + i];
 
-  // ---- B. 4 rows per thread against this CTA's slice.  Rows are paired (r, r + 128) and (r + 256, r + 384) in the two
-  //         halves of packed fma.rn.f32x2 registers; each half runs exactly the scalar chain of the reference order.
-  float2 zp[2][8];           // zp[p][j] = 2 * (z[row_a][j], z[row_b][j])
-  float zz[4];
+  // ---- B. R rows per thread (rows tid + 128 r) against this CTA's slice
+  float z2[R][8];            // 2 * z: (2 * z) @ E^T, the factor 2 is exact
+  float zz[R];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < R; ++r) {
     const float4 za = zsm[2 * (tid + r * VQF_THREADS)], zb = zsm[2 * (tid + r * VQF_THREADS) + 1];
     // sum z^2 exactly as torch's (z**2).sum(dim=1): sequential over the 8 channels
     float s = za.x * za.x;
     s += za.y * za.y; s += za.z * za.z; s += za.w * za.w;
     s += zb.x * zb.x; s += zb.y * zb.y; s += zb.z * zb.z; s += zb.w * zb.w;
     zz[r] = s;
-    const float e[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+    z2[r][0] = 2.f * za.x; z2[r][1] = 2.f * za.y; z2[r][2] = 2.f * za.z; z2[r][3] = 2.f * za.w;
+    z2[r][4] = 2.f * zb.x; z2[r][5] = 2.f * zb.y; z2[r][6] = 2.f * zb.z; z2[r][7] = 2.f * zb.w;
+  }
+  vq_cluster_arrive();          // this CTA's z table is dead: the peers may overwrite it with partial minima (phase C)
+  __syncthreads();              // the table slice is staged
+  float best[R];
+  int bg[R];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {            // (2*z) @ E^T : the factor 2 is exact, fold it into z
-      if (r & 1) zp[r >> 1][j].y = 2.f * e[j]; else zp[r >> 1][j].x = 2.f * e[j];
+  for (int r = 0; r < R; ++r) { best[r] = INFINITY; bg[r] = 0; }
+  for (int g = 0; g < per; g += VQF_GROUP) {
+    float gm[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) gm[r] = INFINITY;
+#pragma unroll
+    for (int c = 0; c < VQF_GROUP; ++c) {
+      const float4 ea = esm[2 * (g + c)], eb = esm[2 * (g + c) + 1];
+      const float ek = e2s[g + c];
+#pragma unroll
+      for (int r = 0; r < R; ++r) gm[r] = fminf(gm[r], vq_dist(z2[r], zz[r], ea, eb, ek));
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (gm[r] < best[r]) { best[r] = gm[r]; bg[r] = g; }          // strict <  => the first group holding the minimum
     }
   }
-  float best[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-  int bi[4] = {0, 0, 0, 0};
-#pragma unroll 2
-  for (int k = 0; k < per; ++k) {
-    const float4 ea = esm[2 * k], eb = esm[2 * k + 1];
-    const float ek = e2s[k];
-    const float ev[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+  // the winning group once more: the first code whose distance equals the minimum bit for bit
+  int bi[R];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      float2 dot = make_float2(zp[p][0].x * ev[0], zp[p][0].y * ev[0]);
+  for (int r = 0; r < R; ++r) {
+    bi[r] = bg[r];
+    bool found = false;
 #pragma unroll
-      for (int j = 1; j < 8; ++j) dot = ffma2(zp[p][j], make_float2(ev[j], ev[j]), dot);
-      const float d0 = (zz[2 * p] - dot.x) + ek, d1 = (zz[2 * p + 1] - dot.y) + ek;
-      if (d0 < best[2 * p]) { best[2 * p] = d0; bi[2 * p] = k; }             // strict <  => first minimum wins
-      if (d1 < best[2 * p + 1]) { best[2 * p + 1] = d1; bi[2 * p + 1] = k; }
+    for (int c = 0; c < VQF_GROUP; ++c) {
+      const float d = vq_dist(z2[r], zz[r], esm[2 * (bg[r] + c)], esm[2 * (bg[r] + c) + 1], e2s[bg[r] + c]);
+      if (!found && d == best[r]) { bi[r] = bg[r] + c; found = true; }
     }
   }
-  // ---- C. partial minima -> the owner CTA of each row
+  // ---- C. partial minima -> the owner CTA of each row (every CTA has left its z table: second cluster barrier)
+  vq_cluster_wait();
   const uint32_t part_s = static_cast<uint32_t>(__cvta_generic_to_shared(part));
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < R; ++r) {
     const int lrow = tid + r * VQF_THREADS;
-    const uint32_t owner = (uint32_t)(lrow / VQF_OWN);
-    const uint32_t dst = vq_mapa(part_s + (uint32_t)((rank * VQF_OWN + (lrow % VQF_OWN)) * 8), owner);
+    const uint32_t owner = (uint32_t)(lrow / OWN);
+    const uint32_t dst = vq_mapa(part_s + (uint32_t)((rank * OWN + (lrow % OWN)) * 8), owner);
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(dst), "f"(best[r]), "f"(__int_as_float(k0 + bi[r])) : "memory");
   }
-  vq_cluster_sync();
-  if (tid < VQF_OWN) {
-    const int row = row0 + (int)rank * VQF_OWN + tid;
+  vq_cluster_arrive();
+  vq_cluster_wait();
+  if (tid < OWN) {
+    const int row = row0 + (int)rank * OWN + tid;
     if (row < M) {
       float2 b0 = part[tid];
 #pragma unroll
       for (int s = 1; s < VQF_SLICES; ++s) {
-        const float2 c = part[s * VQF_OWN + tid];
+        const float2 c = part[s * OWN + tid];
         if (c.x < b0.x) b0 = c;                 // ascending slices, strict <: the first minimum over the whole codebook
       }
       const int code = __float_as_int(b0.y);
@@ -316,28 +344,39 @@ extern "C" int omt_pre_vq(const float* x, int ldx, const float* Wt, const float*
   return OMT_OK;
 }
 
+template <bool PROJECT, int R>
+static int vq_launch_r(const float* x, int ldx, const float* Wt, const float* b, int C, int l2, const float* z_in, float* z_out,
+                       const float* E, const float* e2, int M, int n_codes, int64_t* idx, int32_t* counts, cudaStream_t st) {
+  const int per = n_codes / VQF_SLICES;
+  const size_t smem = (size_t)per * 36 + (size_t)R * VQF_THREADS * 32;
+  OMT_REQUIRE(smem <= 200 * 1024, "omt_vq: n_codes=%d too large for the shared-memory table slice", n_codes);
+  OMT_REQUIRE(!PROJECT || (size_t)8 * C * 4 <= (size_t)per * 36, "omt_vq_fused: C=%d too large for n_codes=%d", C, n_codes);
+  static size_t set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && smem > set[dev]) {
+    OMT_CUDA(cudaFuncSetAttribute(vq_fused_kernel<PROJECT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set[dev] = smem;
+  }
+  const int rows = R * VQF_THREADS;
+  const unsigned blocks = (unsigned)((M + rows - 1) / rows) * VQF_SLICES;
+  OMT_CUDA(launch_k(vq_fused_kernel<PROJECT, R>, dim3(blocks), dim3(VQF_THREADS), smem, st, x, ldx, Wt, b, C, l2, z_in, z_out, E, e2,
+                    M, n_codes, idx, counts));
+  OMT_LAUNCH_CHECK();
+  return OMT_OK;
+}
+
 static int vq_launch(bool project, const float* x, int ldx, const float* Wt, const float* b, int C, int l2, const float* z_in,
                      float* z_out, const float* E, const float* e2, int M, int n_codes, int64_t* idx, int32_t* counts,
                      cudaStream_t st) {
-  OMT_REQUIRE(n_codes % (VQF_SLICES * 4) == 0 && n_codes >= VQF_SLICES * 4, "omt_vq: n_codes %% 32 != 0");
-  const int per = n_codes / VQF_SLICES;
-  const size_t smem = (size_t)per * 36 + VQF_ROWS * 32 + VQF_SLICES * VQF_OWN * 8 + (project ? (size_t)8 * C * 4 : 0);
-  OMT_REQUIRE(smem <= 200 * 1024, "omt_vq: n_codes=%d too large for the shared-memory table slice", n_codes);
-  static size_t set[64][2];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && smem > set[dev][project ? 1 : 0]) {
-    if (project) OMT_CUDA(cudaFuncSetAttribute(vq_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else OMT_CUDA(cudaFuncSetAttribute(vq_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set[dev][project ? 1 : 0] = smem;
-  }
-  const unsigned blocks = (unsigned)((M + VQF_ROWS - 1) / VQF_ROWS) * VQF_SLICES;
+  OMT_REQUIRE(n_codes % (VQF_SLICES * VQF_GROUP) == 0 && n_codes >= VQF_SLICES * VQF_GROUP, "omt_vq: n_codes %% 64 != 0");
+  // 4 rows per thread amortise the table reads best; small inputs take 2 so that more SMs get a cluster
+  const bool small = (M + 4 * VQF_THREADS - 1) / (4 * VQF_THREADS) * VQF_SLICES < omt::sm_count();
   if (project)
-    OMT_CUDA(launch_k(vq_fused_kernel<true>, dim3(blocks), dim3(VQF_THREADS), smem, st, x, ldx, Wt, b, C, l2, z_in, z_out, E, e2, M, n_codes, idx, counts));
-  else
-    OMT_CUDA(launch_k(vq_fused_kernel<false>, dim3(blocks), dim3(VQF_THREADS), smem, st, x, ldx, Wt, b, C, l2, z_in, z_out, E, e2, M, n_codes, idx, counts));
-  OMT_LAUNCH_CHECK();
-  return OMT_OK;
+    return small ? vq_launch_r<true, 2>(x, ldx, Wt, b, C, l2, z_in, z_out, E, e2, M, n_codes, idx, counts, st)
+                 : vq_launch_r<true, 4>(x, ldx, Wt, b, C, l2, z_in, z_out, E, e2, M, n_codes, idx, counts, st);
+  return small ? vq_launch_r<false, 2>(x, ldx, Wt, b, C, l2, z_in, z_out, E, e2, M, n_codes, idx, counts, st)
+               : vq_launch_r<false, 4>(x, ldx, Wt, b, C, l2, z_in, z_out, E, e2, M, n_codes, idx, counts, st);
 }
 
 extern "C" int omt_vq_search(const float* z, const float* E, const float* e2, int M, int n_codes,

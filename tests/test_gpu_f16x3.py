@@ -331,10 +331,13 @@ def _static_planes(x, ps):
     return hi, (xs - hi.float()).half()
 
 
+@pytest.mark.parametrize("ramp", [False, True])
 @pytest.mark.parametrize("N", [128, 256, 1024])
-def test_attn_spatial_h(cuda, N):
+def test_attn_spatial_h(cuda, N, ramp):
     """tcgen05 kind::f16 attention core on operand planes (Q / P in tensor memory, V as MN-major B) vs fp64 softmax;
-    q, k unit-norm x scale as the QKV epilogue leaves them, v rows of very different magnitude."""
+    q, k unit-norm x scale as the QKV epilogue leaves them, v rows of very different magnitude.  ramp: key norms grow
+    along the sequence so that the row maxima keep rising from tile to tile -- the in-place rescale of the O accumulator
+    (lazy running maximum) fires several times per row."""
     cabi = _cabi(0)
     from omnitokenizer_b200 import layout as L
     nseq, H = 3, 8
@@ -342,6 +345,8 @@ def test_attn_spatial_h(cuda, N):
     g = torch.Generator().manual_seed(40 + N)
     q = torch.nn.functional.normalize(torch.randn(M, H, 64, generator=g), dim=-1) * (torch.rand(64, generator=g) + 0.5)
     k = torch.nn.functional.normalize(torch.randn(M, H, 64, generator=g), dim=-1) * (torch.rand(64, generator=g) + 0.5)
+    if ramp:
+        k = k * (0.1 + 2.4 * (torch.arange(M) % N).float() / N)[:, None, None]
     v = torch.randn(M, H, 64, generator=g) * torch.logspace(-2, 2, M)[torch.randperm(M, generator=g)][:, None, None]
     qs, ks = L.pow2_scale(float(q.abs().max())), L.pow2_scale(float(k.abs().max()))
     qh, ql = _static_planes(q.reshape(M, 512), qs)

@@ -322,6 +322,19 @@ def test_vq_path(cuda):
         bad = (idx2.cpu() != out["idx"][:Mf]).nonzero().flatten()
         assert bad.numel() == 0, f"fused idx differs at M={Mf}: {bad.numel()} rows, first {bad[:8].tolist()} got {idx2.cpu()[bad[:8]].tolist()} want {out['idx'][bad[:8]].tolist()}"
         assert torch.equal(counts.cpu().long(), torch.bincount(out["idx"][:Mf], minlength=8192))
+    # the 4-rows-per-thread form (taken when the launch fills the GPU): 12 000 rows, with duplicated codes in different slices
+    Mb = 12000
+    xb = _rand((Mb, C), 66)
+    zb = torch.empty(Mb, 8, device=cuda)
+    idxb = torch.full((Mb,), -1, dtype=torch.int64, device=cuda)
+    counts.zero_()
+    cabi.call("omt_vq_fused", xb.to(cuda), C, Wp.to(cuda), bp.to(cuda), C, 1, zb, E2.to(cuda), e22.to(cuda), Mb, 8192, idxb, counts)
+    want = oo.codebook(E2, zb.cpu())["idx"]
+    assert torch.equal(idxb.cpu(), want) and int(idxb.max()) < 4096
+    assert torch.equal(counts.cpu().long(), torch.bincount(want, minlength=8192))
+    idxc = torch.full((Mb,), -1, dtype=torch.int64, device=cuda)
+    cabi.call("omt_vq_search", zb, E.to(cuda), e2.to(cuda), Mb, 8192, idxc, None)
+    assert torch.equal(idxc.cpu(), oo.codebook(E, zb.cpu())["idx"])
     # decode-side gather + post_vq, with and without straight-through rounding
     Wq, bq = _rand((512, 8), 64, 0.3), _rand((512,), 65, 0.1)
     X = torch.empty(M, 512, device=cuda)
