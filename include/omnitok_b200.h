@@ -233,11 +233,13 @@ int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, 
                     int M, int C, float eps, int seg, int seg_stride, int seg_off, omt_stream_t stream);
 
 /* Tuning knobs (process-wide): "pdl" = 0 (default; measured 2-4 % slower when on) | 1 programmatic dependent launch;
- * "peg_kernel" = 3 (default) | 4 (cp.async gather + packed f32x2 FMAs) | 5 (4 inside a persistent CTA that double-buffers the
- * halo tile); all three produce identical bits;
+ * "peg_kernel" = 4 (default: cp.async zero-fill halo gather + packed f32x2 FMAs) | 3 (register-staged gather; also the
+ * fallback for T > 64 or w > 254); identical bits;
  * "attn_kernel" = 3 (default: tcgen05 spatial attention core when N % 128 == 0) | 1 (CUDA-core fp32);
  * "f16_bn" = 0 (default: by shape) | 256 (256 x 256 tiles, one TMEM buffer released as soon as the epilogue has drained
- * it into registers) | 128 (256 x 128 tiles, double-buffered accumulators): tile width of omt_linear_h's two-accumulator form. */
+ * it into registers) | 128 (256 x 128 tiles, double-buffered accumulators): tile width of omt_linear_h's two-accumulator form;
+ * "attn_f16_ctas" = 1 (default: double-buffered S / P, one CTA per SM) | 2 (single buffers, 256 TMEM columns, two CTAs per SM):
+ * shape of omt_attn_spatial_h's kernel; identical results. */
 int omt_set_option(const char* name, int value);
 
 #ifdef __cplusplus

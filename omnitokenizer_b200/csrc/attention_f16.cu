@@ -24,16 +24,23 @@
 #include <cuda.h>
 
 namespace omt {
+int g_attn_f16_ctas = 1;      // omt_set_option("attn_f16_ctas", 1 | 2): CTAs per SM of the f16 attention core
 namespace af16 {
 using namespace omt::ptx;
 
 constexpr int QT = 128, KT = 64, D = 64;
 constexpr int TILE = KT * D * 2;                    // 8 KiB: one 64 x 64 fp16 plane tile
 constexpr int STAGE_BYTES = 4 * TILE + 1024;        // K_hi, K_lo, V_hi, V_lo + vinv (256 B, padded to keep 1024-B alignment)
-constexpr int STAGES = 4;
-constexpr int OFF_CTRL = STAGES * STAGE_BYTES;
-constexpr int SMEM = OFF_CTRL + 3072 + 1024;        // barriers / exchange + alignment slack
-constexpr int TM_S = 0, TM_O = 128, TM_P = 256, TM_Q = 384;
+// Two shapes of the same kernel.  NB = 2: S and P double-buffered, 4 K/V stages, all 512 TMEM columns, one CTA per SM.
+// NB = 1: single S / P buffers, 2 stages, 256 TMEM columns, 95 registers -> TWO CTAs per SM: the softmax threads of one
+// CTA cover the tensor-memory round trips and barriers of the other (the tile loop is latency-bound, not issue-bound).
+template <int NB> struct Cfg {
+  static constexpr int STAGES = NB == 2 ? 4 : 2;
+  static constexpr int OFF_CTRL = STAGES * STAGE_BYTES;
+  static constexpr int SMEM = OFF_CTRL + 3072 + 1024;      // barriers / exchange + alignment slack
+  static constexpr int TM_S = 0, TM_O = 64 * NB, TM_P = TM_O + 64, TM_Q = TM_P + 64 * NB;
+  static constexpr int TM_COLS = NB == 2 ? 512 : 256;
+};
 constexpr int THREADS = 64 + 256;                   // TMA, MMA, 8 softmax warps
 constexpr uint32_t IDESC_S = idesc_f16(128, 64, false, false);                      // A: TMEM, B: K-major smem
 constexpr uint32_t IDESC_PV = idesc_f16(128, 64, false, false) | (1u << 16);        // B (= V tile) is MN-major
@@ -70,9 +77,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* u) {
         "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int NB>
+__global__ void __launch_bounds__(THREADS, 3 - NB)
 attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                 const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, const Args a) {
+  constexpr int STAGES = Cfg<NB>::STAGES, OFF_CTRL = Cfg<NB>::OFF_CTRL;
+  constexpr int TM_S = Cfg<NB>::TM_S, TM_O = Cfg<NB>::TM_O, TM_P = Cfg<NB>::TM_P, TM_Q = Cfg<NB>::TM_Q;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTRL);
@@ -108,7 +118,7 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(Cfg<NB>::TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -140,9 +150,9 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
     const uint32_t sb = smem_u32(smem);
     const uint32_t tq_hi = tmem_base + TM_Q, tq_lo = tmem_base + TM_Q + 32;
     auto issue_s = [&](int j) {
-      const int s = j % STAGES, b = j & 1;
+      const int s = j % STAGES, b = j % NB;
       mbar_wait(&full[s], (j / STAGES) & 1);
-      mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+      mbar_wait(&s_empty[b], ((j / NB) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d = tmem_base + TM_S + b * 64;
@@ -162,8 +172,8 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
     issue_s(0);
     for (int j = 0; j < ntiles; ++j) {
       if (j + 1 < ntiles) issue_s(j + 1);
-      const int s = j % STAGES, b = j & 1;
-      const uint32_t ph2 = (j >> 1) & 1;
+      const int s = j % STAGES, b = j % NB;
+      const uint32_t ph2 = (j / NB) & 1;
       mbar_wait(&p_full[b], ph2);
       tc_fence_after();
       if (elect_one()) {
@@ -231,10 +241,10 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
     float m_used = -INFINITY, l_run = 0.f;
     const uint32_t o_addr = tmem_base + TM_O + lane_addr + half * 32;
     for (int j = 0; j < ntiles; ++j) {
-      const int b = j & 1, s = j % STAGES;
+      const int b = j % NB, xb = j & 1, s = j % STAGES;
       float sv[32];
       mbar_wait(&full[s], (j / STAGES) & 1);         // the tile's vinv slice (read below) has landed
-      mbar_wait(&s_full[b], (j >> 1) & 1);
+      mbar_wait(&s_full[b], (j / NB) & 1);
       tc_fence_after();
       tmem_ld32(tmem_base + TM_S + lane_addr + b * 64 + half * 32, sv);
       tc_fence_before();
@@ -245,17 +255,17 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
       for (int i = 1; i < 32; ++i) mx = fmaxf(mx, sv[i]);
       // the slot alternates with the tile parity: the partner passes the NEXT tile's barrier only after this read, and
       // that barrier comes before anyone writes this slot again -- one barrier per tile is enough
-      xch[(b * 2 + half) * QT + r] = mx;
+      xch[(xb * 2 + half) * QT + r] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(mx, xch[(b * 2 + (half ^ 1)) * QT + r]);
+      mx = fmaxf(mx, xch[(xb * 2 + (half ^ 1)) * QT + r]);
       const bool grow = (mx - m_used) * a.scale_log2 > TAU;          // always true on the first tile (m_used = -inf)
       float alpha = 1.f;
       if (grow) { alpha = ex2_fast((m_used - mx) * a.scale_log2); m_used = mx; }
-      if (j >= 2) mbar_wait(&o_full[b], ((j - 2) >> 1) & 1);         // P.V of tile j-2 no longer reads this P buffer
+      if (j >= NB) mbar_wait(&o_full[b], ((j - NB) / NB) & 1);       // P.V of tile j-NB no longer reads this P buffer
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
         // rescale this warp's O rows in place: every P.V issued so far (tile j-1 is the last) must have retired, and P.V(j)
         // is not issued before all eight warps have arrived on p_full below
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        mbar_wait(&o_full[(j - 1) % NB], ((j - 1) / NB) & 1);
         tc_fence_after();
         float ov[32];
         tmem_ld32(o_addr, ov);
@@ -298,7 +308,7 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
     float o_acc[32];
     {
       const int jp = ntiles - 1;
-      mbar_wait(&o_full[jp & 1], (jp >> 1) & 1);
+      mbar_wait(&o_full[jp % NB], (jp / NB) & 1);
       tc_fence_after();
       tmem_ld32(o_addr, o_acc);
       tc_fence_before();
@@ -320,7 +330,7 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg<NB>::TM_COLS) : "memory");
   }
 }
 
@@ -379,12 +389,16 @@ extern "C" int omt_attn_spatial_h(const uint16_t* q_hi, const uint16_t* q_lo, in
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr[dev]) {
-    OMT_CUDA(cudaFuncSetAttribute(attn_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    OMT_CUDA(cudaFuncSetAttribute(attn_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM));
+    OMT_CUDA(cudaFuncSetAttribute(attn_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM));
     attr[dev] = true;
   }
   Args a{q_hi, q_lo, ldq, vinv, rows, o, o_hi, o_lo, ldo, N, scale * 1.4426950408889634f / qk_plane_scale};
   dim3 grid(N / QT, heads, n_seq);
-  OMT_CUDA(launch_k(attn_f16_kernel, grid, dim3(THREADS), SMEM, (cudaStream_t)stream, tmKh, tmKl, tmVh, tmVl, a));
+  if (g_attn_f16_ctas == 2)
+    OMT_CUDA(launch_k(attn_f16_kernel<1>, grid, dim3(THREADS), Cfg<1>::SMEM, (cudaStream_t)stream, tmKh, tmKl, tmVh, tmVl, a));
+  else
+    OMT_CUDA(launch_k(attn_f16_kernel<2>, grid, dim3(THREADS), Cfg<2>::SMEM, (cudaStream_t)stream, tmKh, tmKl, tmVh, tmVl, a));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }

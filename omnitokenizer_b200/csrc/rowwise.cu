@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int g_peg_kernel = 3;   // omt_set_option("peg_kernel", 3|4): 3 = peg_tile_kernel, 4 = peg_tile4_kernel (cp.async + FFMA2)
+int g_peg_kernel = 4;   // omt_set_option("peg_kernel", 3|4): 4 = peg_tile4_kernel (cp.async gather + FFMA2, default), 3 = peg_tile_kernel
 int g_pdl = 0;   // measured on B200: PDL made the step 2-4 % slower (dependent CTAs hold SM resources during the tail), so it is opt-in
 static int g_dev_ok[64];   // 0 unknown, 1 ok, -1 bad
 static int g_sms[64];
@@ -581,140 +581,6 @@ __global__ void __launch_bounds__(256) peg_tile4_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// PEG, tiled form v5: the v4 arithmetic (same fma order: bit-identical to v3 / v4) inside a PERSISTENT CTA that
-// double-buffers the halo tile: while tile i is evaluated out of buffer i & 1, the cp.async gather of tile i + 1 fills
-// the other buffer, so the global-load latency that v3 / v4 expose once per CTA (their CTAs load, wait, compute; ncu:
-// 13 % of the stall samples on the first shared store after the gather, 14 % occupancy) is hidden behind compute.
-// Two threads share a strip (each takes half of the w range), 320 threads per CTA, one CTA per SM.
-// ------------------------------------------------------------------------------------------
-struct PegGeom { int T, h, w, C, temporal, causal, TT, HB, RS, n_tblk, n_hblk, n_cg, B; };
-
-__device__ __forceinline__ void peg5_gather(const float* __restrict__ x, const PegGeom& g, int tile, uint32_t buf_s) {
-  const int N = g.h * g.w;
-  const int cg = tile % g.n_cg;
-  int r = tile / g.n_cg;
-  const int hb = r % g.n_hblk; r /= g.n_hblk;
-  const int tb = r % g.n_tblk;
-  const int b = r / g.n_tblk;
-  const int t0 = tb * g.TT, h0 = hb * g.HB, c0 = cg * PEG_CC;
-  const long long bbase = (long long)b * g.T * N;
-  const int pad_lo = g.causal ? 2 : 1;
-  const int rows = (g.TT + 2) * (g.HB + 2);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const uint32_t inv_T = (65536u + (uint32_t)g.T - 1u) / (uint32_t)g.T;
-  const int chunks = (g.w + 2) * 4;
-  for (int pr = warp; pr < rows; pr += nwarps) {
-    const int ph = pr % (g.HB + 2), pt = pr / (g.HB + 2);
-    const int t2 = t0 - pad_lo + pt, h2 = h0 - 1 + ph;
-    const bool row_ok = t2 >= 0 && t2 < g.T && h2 >= 0 && h2 < g.h;
-    const int fb = row_ok ? (t2 * g.h + h2) * g.w : 0;
-    const int tau0 = fb % g.T, nn0 = fb / g.T;
-    const uint32_t dst_row = buf_s + (uint32_t)(pr * g.RS) * 4u;
-    for (int j = lane; j < chunks; j += 32) {
-      const int w2 = (j >> 2) - 1;
-      const bool ok = row_ok && w2 >= 0 && w2 < g.w;
-      long long row = 0;
-      if (ok) {
-        if (g.temporal) {
-          const uint32_t v = (uint32_t)(tau0 + w2);
-          const uint32_t q = (v * inv_T) >> 16;
-          row = (long long)(v - q * (uint32_t)g.T) * N + nn0 + (int)q;
-        } else {
-          row = fb + w2;
-        }
-      }
-      const float* src = x + (bbase + row) * g.C + c0 + (j & 3) * 4;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_row + (uint32_t)j * 16u), "l"(src), "r"(ok ? 16 : 0) : "memory");
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(320, 1) peg_tile5_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                           const float* __restrict__ w27, const float* __restrict__ bias,
-                                                           const PegGeom g, const int n_tiles) {
-  pdl_sync();
-  extern __shared__ __align__(16) float tile[];      // 2 x [(TT+2)][(HB+2)] rows of RS floats
-  const int N = g.h * g.w;
-  const int rows = (g.TT + 2) * (g.HB + 2);
-  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
-  const uint32_t buf_bytes = (uint32_t)(rows * g.RS) * 4u;
-  const int cp = threadIdx.x & 7;                  // channel pair inside the 16-channel slab
-  const int sidx = threadIdx.x >> 3;
-  const int nstrip = g.TT * g.HB;
-  const int strip = sidx % nstrip, seg = sidx / nstrip;        // two threads per strip: w halves
-  const int sh = strip % g.HB, st = strip / g.HB;
-  const int wh = (g.w + 1) >> 1;
-  const int w_lo = seg * wh, w_hi = min(g.w, w_lo + wh);
-  const bool cz = g.causal != 0;
-
-  int tile_i = blockIdx.x;
-  if (tile_i < n_tiles) peg5_gather(x, g, tile_i, tile_s);
-  for (int it = 0; tile_i < n_tiles; tile_i += gridDim.x, ++it) {
-    const uint32_t buf = tile_s + (uint32_t)(it & 1) * buf_bytes;
-    const int next = tile_i + gridDim.x;
-    if (next < n_tiles) {
-      peg5_gather(x, g, next, tile_s + (uint32_t)((it + 1) & 1) * buf_bytes);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    // ---- this tile's coordinates
-    const int cg = tile_i % g.n_cg;
-    int r = tile_i / g.n_cg;
-    const int hb = r % g.n_hblk; r /= g.n_hblk;
-    const int tb = r % g.n_tblk;
-    const int b = r / g.n_tblk;
-    const int t0 = tb * g.TT, h0 = hb * g.HB, c0 = cg * PEG_CC;
-    const long long bbase = (long long)b * g.T * N;
-    const bool active = seg < 2 && st < g.TT && t0 + st < g.T && h0 + sh < g.h && w_lo < w_hi;
-    if (active) {
-      float2 wt[27];
-#pragma unroll
-      for (int k = 0; k < 27; ++k) wt[k] = __ldg(reinterpret_cast<const float2*>(w27 + (size_t)k * g.C + c0 + 2 * cp));
-      const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0 + 2 * cp));
-      // shared byte addresses of halo column w_lo (= w2 - 1 of the first output) of the 9 window rows of this strip
-      uint32_t a[9];
-      {
-        const uint32_t base = buf + (uint32_t)(((st * (g.HB + 2) + sh) * g.RS + w_lo * PEG_CC + 2 * cp) * 4);
-#pragma unroll
-        for (int r9 = 0; r9 < 9; ++r9) a[r9] = base + (uint32_t)((((r9 / 3) * (g.HB + 2) + r9 % 3) * g.RS) * 4);
-      }
-      float2 win[9][3];
-#pragma unroll
-      for (int r9 = 0; r9 < 9; ++r9) {
-        win[r9][0] = lds_f2(a[r9]);
-        win[r9][1] = lds_f2(a[r9] + PEG_CC * 4);
-        a[r9] += 2 * PEG_CC * 4;
-      }
-      const int fbase = ((t0 + st) * g.h + (h0 + sh)) * g.w + w_lo;
-      int tau = fbase % g.T;
-      const long long row0 = g.temporal ? (long long)tau * N + fbase / g.T : (long long)fbase;
-      float* yp = y + (bbase + row0) * g.C + c0 + 2 * cp;
-      const long long inc = g.temporal ? (long long)N * g.C : (long long)g.C;
-      const long long wrap = (long long)g.T * N * g.C - g.C;
-#define OMT_PEG5_STEP(R)                                                                            \
-      {                                                                                             \
-        const float2 acc = peg_step<R>(win, wt, bb, a, cz);                                         \
-        *reinterpret_cast<float2*>(yp) = acc;                                                       \
-        yp += inc;                                                                                  \
-        if (g.temporal && ++tau == g.T) { tau = 0; yp -= wrap; }                                    \
-      }
-      for (int wb = w_lo; wb < w_hi; wb += 3) {
-        OMT_PEG5_STEP(0)
-        if (wb + 1 < w_hi) OMT_PEG5_STEP(1)
-        if (wb + 2 < w_hi) OMT_PEG5_STEP(2)
-#pragma unroll
-        for (int r9 = 0; r9 < 9; ++r9) a[r9] += 3 * PEG_CC * 4;
-      }
-#undef OMT_PEG5_STEP
-    }
-    __syncthreads();           // everyone is done with this buffer before the gather two tiles ahead refills it
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // rope + l2norm + scale, in place on q and k.  One warp per row; lane l owns the complex pair
 // (2l, 2l+1) of every head.
 // ------------------------------------------------------------------------------------------
@@ -927,23 +793,6 @@ extern "C" int omt_peg_volume(const float* x, float* y, const float* w27, const 
   const int threads = ((TT * HB * 8 + 31) / 32) * 32;
   dim3 grid(((T + TT - 1) / TT) * ((h + HB - 1) / HB), C / PEG_CC, B);
   const bool fast_ok = T <= 64 && w <= 254 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  const size_t smem5 = 2 * (size_t)(TT + 2) * (HB + 2) * RS * sizeof(float);       // two halo buffers, no position map
-  if (g_peg_kernel == 5 && fast_ok && smem5 <= 220 * 1024 && 2 * TT * HB * 8 <= 320) {
-    static size_t smem5_set[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && smem5 > smem5_set[dev]) {
-      OMT_CUDA(cudaFuncSetAttribute(peg_tile5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-      smem5_set[dev] = smem5;
-    }
-    PegGeom pg{T, h, w, C, temporal, causal, TT, HB, RS, (T + TT - 1) / TT, (h + HB - 1) / HB, C / PEG_CC, B};
-    const int n_tiles = pg.n_tblk * pg.n_hblk * pg.n_cg * B;
-    int blocks = omt::sm_count();
-    if (blocks > n_tiles) blocks = n_tiles;
-    OMT_CUDA(launch_k(peg_tile5_kernel, dim3(blocks), dim3(320), smem5, (cudaStream_t)stream, x, y, w27, bias, pg, n_tiles));
-    OMT_LAUNCH_CHECK();
-    return OMT_OK;
-  }
   const bool v4 = g_peg_kernel == 4 && fast_ok;
   if (v4) {
     static size_t smem4_set = 0;
@@ -973,13 +822,13 @@ extern "C" int omt_qk_prep(float* q, int ldq, float* k, int ldk, const float* q_
   return OMT_OK;
 }
 
-namespace omt { extern int g_attn_kernel; extern int g_f16_bn; }
+namespace omt { extern int g_attn_kernel; extern int g_f16_bn; extern int g_attn_f16_ctas; }
 
 extern "C" int omt_set_option(const char* name, int value) {
   if (name == nullptr) return OMT_E_ARG;
   if (strcmp(name, "pdl") == 0) { omt::g_pdl = value ? 1 : 0; return OMT_OK; }
   if (strcmp(name, "peg_kernel") == 0) {
-    if (value < 3 || value > 5) { omt::set_error("peg_kernel must be 3, 4 or 5"); return OMT_E_ARG; }
+    if (value != 3 && value != 4) { omt::set_error("peg_kernel must be 3 or 4"); return OMT_E_ARG; }
     omt::g_peg_kernel = value;
     return OMT_OK;
   }
@@ -991,6 +840,11 @@ extern "C" int omt_set_option(const char* name, int value) {
   if (strcmp(name, "f16_bn") == 0) {
     if (value != 0 && value != 128 && value != 256) { omt::set_error("f16_bn must be 0, 128 or 256"); return OMT_E_ARG; }
     omt::g_f16_bn = value;
+    return OMT_OK;
+  }
+  if (strcmp(name, "attn_f16_ctas") == 0) {
+    if (value != 1 && value != 2) { omt::set_error("attn_f16_ctas must be 1 or 2"); return OMT_E_ARG; }
+    omt::g_attn_f16_ctas = value;
     return OMT_OK;
   }
   omt::set_error("unknown option %s", name);

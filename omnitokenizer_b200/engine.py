@@ -106,10 +106,11 @@ class Engine:
     def __init__(self, model, device: torch.device, math: Optional[str] = None):
         _cabi.load()
         _cabi.set_option("pdl", int(os.environ.get("OMT_PDL", "0")))     # programmatic dependent launch between kernels
-        if os.environ.get("OMT_PEG_KERNEL"):                             # 3 | 4, tuning knob (default: the library's)
-            _cabi.set_option("peg_kernel", int(os.environ["OMT_PEG_KERNEL"]))
-        if os.environ.get("OMT_F16_BN"):                                 # 128 | 256, tile N of the f16x3 GEMM (tuning knob)
-            _cabi.set_option("f16_bn", int(os.environ["OMT_F16_BN"]))
+        # process-wide kernel selectors (tuning knobs; see omt_set_option): the environment or the library default
+        for env, opt in (("OMT_PEG_KERNEL", "peg_kernel"),        # 4 (cp.async gather, default) | 3
+                         ("OMT_ATTN_CTAS", "attn_f16_ctas"),      # CTAs per SM of the f16 attention core
+                         ("OMT_F16_BN", "f16_bn")):               # 0 (by shape) | 128 | 256: tile N of the two-accumulator GEMM form
+            _cabi.set_option(opt, int(os.environ.get(env) or _cabi.DEFAULT_OPTIONS[opt]))
         self.device = device
         self.math_name = (math or default_math()).lower()
         if self.math_name not in MATH_MODES:

@@ -331,14 +331,16 @@ def _static_planes(x, ps):
     return hi, (xs - hi.float()).half()
 
 
+@pytest.mark.parametrize("ctas", [1, 2])
 @pytest.mark.parametrize("ramp", [False, True])
 @pytest.mark.parametrize("N", [128, 256, 1024])
-def test_attn_spatial_h(cuda, N, ramp):
+def test_attn_spatial_h(cuda, N, ramp, ctas):
     """tcgen05 kind::f16 attention core on operand planes (Q / P in tensor memory, V as MN-major B) vs fp64 softmax;
     q, k unit-norm x scale as the QKV epilogue leaves them, v rows of very different magnitude.  ramp: key norms grow
     along the sequence so that the row maxima keep rising from tile to tile -- the in-place rescale of the O accumulator
     (lazy running maximum) fires several times per row."""
     cabi = _cabi(0)
+    cabi.set_option("attn_f16_ctas", ctas)           # both shapes of the kernel (conftest restores the default)
     from omnitokenizer_b200 import layout as L
     nseq, H = 3, 8
     M = nseq * N

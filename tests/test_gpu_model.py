@@ -18,15 +18,19 @@ def _math_modes():
     return [m for m in os.environ.get("OMT_TEST_MATH", "fp32,3xtf32,f16x3").split(",") if m]
 
 
-VARIANTS = {"base": dict(OMT_ATTN_F16="0", OMT_STATIC_U="0", OMT_PEG_KERNEL="3"),
-            # fp16-plane attention core, statically scaled GEGLU planes (single-accumulator FF2), persistent PEG
-            "fast": dict(OMT_ATTN_F16="1", OMT_STATIC_U="1", OMT_PEG_KERNEL="5"),
-            "upeg": dict(OMT_ATTN_F16="0", OMT_STATIC_U="1", OMT_PEG_KERNEL="5")}      # bring-up: fast minus the attention core
+VARIANTS = {"base": dict(OMT_ATTN_F16="0", OMT_STATIC_U="0", OMT_PEG_KERNEL="3", OMT_ATTN_CTAS="1"),
+            # the shipped defaults: fp16-plane attention core, cp.async PEG
+            "default": dict(),
+            # every optional kernel: statically scaled GEGLU planes (single-accumulator FF2), two attention CTAs per SM
+            "fast": dict(OMT_ATTN_F16="1", OMT_STATIC_U="1", OMT_PEG_KERNEL="4", OMT_ATTN_CTAS="2")}
 
 
-@pytest.fixture(autouse=True, params=[v for v in os.environ.get("OMT_TEST_VARIANTS", "base,fast").split(",") if v])
+@pytest.fixture(autouse=True, params=[v for v in os.environ.get("OMT_TEST_VARIANTS", "base,default,fast").split(",") if v])
 def _kernel_variant(request, monkeypatch):
-    """every model-level test runs with the conservative kernel set and with the fast one (the latter only differs in f16x3 math)"""
+    """every model-level test runs with the conservative kernel set, the shipped defaults and every optional kernel on (the
+    sets only differ in f16x3 math)"""
+    for k in ("OMT_ATTN_F16", "OMT_STATIC_U", "OMT_PEG_KERNEL", "OMT_ATTN_CTAS"):
+        monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[request.param].items():
         monkeypatch.setenv(k, v)
     yield

@@ -154,7 +154,7 @@ def test_layernorm_and_patchify(cuda):
             assert torch.equal(got_v, want_v)
 
 
-@pytest.mark.parametrize("pk", [3, 4, 5])
+@pytest.mark.parametrize("pk", [3, 4])
 @pytest.mark.parametrize("temporal", [False, True])
 @pytest.mark.parametrize("T", [1, 5])
 def test_peg(cuda, temporal, T, pk):
@@ -183,22 +183,22 @@ def test_peg(cuda, temporal, T, pk):
                                                    (5, 32, 32, False, True), (5, 32, 32, True, True),
                                                    (3, 6, 9, False, True), (17, 8, 8, True, True), (1, 32, 32, False, True)])
 def test_peg_volume_shapes(cuda, T, h, w, temporal, causal):
-    """The tiled kernels against the oracle; v4 (cp.async + FFMA2) and v5 (v4 in a persistent, double-buffered CTA) keep
-    v3's fma order, so all three are bit-identical."""
+    """The tiled kernels against the oracle; v4 (cp.async + FFMA2, the default) keeps v3's fma order, so the two are
+    bit-identical."""
     cabi = _cabi()
     B, C = 2, 64
     X = _rand((B, T, h * w, C), 23)
     wt, bias = _rand((C, 1, 3, 3, 3), 24, 0.3), _rand((C,), 25, 0.1)
     want = oo.peg(X, wt, bias, (h, w), temporal, causal) + X
     got = {}
-    for pk in (3, 4, 5):
+    for pk in (3, 4):
         cabi.set_option("peg_kernel", pk)
         y = torch.full((B * T * h * w, C), float("nan"), device=cuda)
         cabi.call("omt_peg_volume", X.reshape(-1, C).to(cuda), y, wt.reshape(C, 27).t().contiguous().to(cuda),
                   bias.to(cuda), B, T, h, w, C, int(temporal), int(causal))
         got[pk] = y.cpu()
         assert (got[pk].view_as(want) - want).abs().max().item() < 1e-5, pk
-    assert torch.equal(got[3], got[4]) and torch.equal(got[3], got[5])
+    assert torch.equal(got[3], got[4])
 
 
 def _attn_inputs(M, seed):
