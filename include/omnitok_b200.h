@@ -238,7 +238,7 @@ int omt_layernorm_h(const float* x, int ldx, float* y, int ldy, uint16_t* y_hi, 
  * "attn_kernel" = 3 (default: tcgen05 spatial attention core when N % 128 == 0) | 1 (CUDA-core fp32);
  * "f16_bn" = 0 (default: by shape) | 256 (256 x 256 tiles, one TMEM buffer released as soon as the epilogue has drained
  * it into registers) | 128 (256 x 128 tiles, double-buffered accumulators): tile width of omt_linear_h's two-accumulator form;
- * "attn_f16_ctas" = 1 (default: double-buffered S / P, one CTA per SM) | 2 (single buffers, 256 TMEM columns, two CTAs per SM):
+ * "attn_f16_ctas" = 2 (default: single S / P buffers, 256 TMEM columns, two CTAs per SM) | 1 (double-buffered S / P, one CTA per SM):
  * shape of omt_attn_spatial_h's kernel; identical results. */
 int omt_set_option(const char* name, int value);
 

@@ -142,7 +142,7 @@ def linear_h(**kw):
 
 
 # process-wide kernel selectors and their library defaults (omt_set_option); tests restore these after flipping them
-DEFAULT_OPTIONS = {"attn_kernel": 3, "peg_kernel": 4, "f16_bn": 0, "attn_f16_ctas": 1}
+DEFAULT_OPTIONS = {"attn_kernel": 3, "peg_kernel": 4, "f16_bn": 0, "attn_f16_ctas": 2}
 
 
 def set_option(name: str, value: int):

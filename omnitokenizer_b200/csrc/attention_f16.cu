@@ -9,17 +9,18 @@
 //          the inverse scales live in vinv[head][row]
 // so S = Q K^T and O_j = P_j V_j each take THREE kind::f16 MMAs per 16-deep k-step into ONE fp32 accumulator
 // (hi.hi + hi.lo + lo.hi) -- half the MMAs of the 3xTF32 core, 16-deep instead of 8-deep.
-//   * P is a TENSOR-MEMORY A operand (two fp16 per 32-bit column); Q, K and V come from shared memory straight from TMA --
-//     no transform warps at all.  (Q was a TMEM operand first: with N = 64 an MMA retires in 32 cycles but reads 4 KiB of
-//     A, and tensor memory delivers 64 B/clk, so the 24 TS-form MMAs + the S read-back of a key tile cost 2 048 cycles of
-//     TMEM reads against 768 of tensor pipe.  With Q in shared memory the TMEM reads drop to 1 280 cycles per tile.)
+//   * Q and P are TENSOR-MEMORY A operands (two fp16 per 32-bit column): only the K / V B tiles come from shared
+//     memory, straight from TMA -- no transform warps at all.
 //   * V is consumed as an MN-MAJOR B operand: the token-major tile [64 keys][64 dims] the TMA lands is exactly the
 //     canonical SWIZZLE_128B MN-major layout, so nothing is transposed anywhere.
 //   * the per-key inverse V scale is folded into P: P'' = p * vinv_j * 2^ep with ONE power of two per CTA taken from the
 //     largest vinv of the sequence, so p'' stays in fp16 range; 2^-ep comes off with the final 1 / row-sum.
-//   TMEM columns (NB = 2): S[2] 0-127 | O 128-191 (accumulates over the key tiles) | P[2] x (hi 32 | lo 32) 192-319
-//   smem        : Q_hi | Q_lo (16 KiB each, loaded once) ; per stage K_hi | K_lo | V_hi | V_lo (8 KiB each) | vinv (256 B),
-//                 every tile one TMA transaction set
+//   TMEM columns: S[2] 0-127 | O 128-191 (accumulates over the key tiles) | P[2] x (hi 32 | lo 32) 256-383 | Q (hi 32 | lo 32) 384-447
+//   smem stage  : K_hi | K_lo | V_hi | V_lo (8 KiB each) | vinv (256 B), 4 stages, every tile one TMA transaction set
+// Measured alternatives (same box, same process, `scripts/bench_attn.py`, cfg-3 shape, two CTAs per SM): Q as a shared-memory
+// operand (SS-form S MMAs) 299 us vs 288 us for this form; P_hi.[V_hi | V_lo] as one N = 128 MMA: no gain with one CTA per SM and
+// 2.7x slower with two.  The tile loop is bound by the serial chain S read-back -> max -> exp -> P write of the softmax threads,
+// not by tensor-pipe or tensor-memory throughput (ncu: tensor pipe 30 %, issue slots 38 %), hence two CTAs per SM.
 // Roles: warp 0 TMA, warp 1 MMA issue + TMEM alloc, warps 2-9 softmax: TWO threads per query row (32 keys / 32 output
 //        dims each; they only exchange the row max), S from TMEM, P back to TMEM, O read back once at the end.
 #include "omt_common.cuh"
@@ -27,30 +28,29 @@
 #include <cuda.h>
 
 namespace omt {
-int g_attn_f16_ctas = 1;      // omt_set_option("attn_f16_ctas", 1 | 2): CTAs per SM of the f16 attention core
+int g_attn_f16_ctas = 2;      // omt_set_option("attn_f16_ctas", 1 | 2): CTAs per SM of the f16 attention core (2 = default)
 namespace af16 {
 using namespace omt::ptx;
 
 constexpr int QT = 128, KT = 64, D = 64;
 constexpr int TILE = KT * D * 2;                    // 8 KiB: one 64 x 64 fp16 plane tile
-constexpr int QTILE = QT * D * 2;                   // 16 KiB: the 128 x 64 query tile of one plane
 constexpr int STAGE_BYTES = 4 * TILE + 1024;        // K_hi, K_lo, V_hi, V_lo + vinv (256 B, padded to keep 1024-B alignment)
 // Two shapes of the same kernel.  NB = 2: S and P double-buffered, 4 K/V stages, all 512 TMEM columns, one CTA per SM.
 // NB = 1: single S / P buffers, 2 stages, 256 TMEM columns, 95 registers -> TWO CTAs per SM: the softmax threads of one
 // CTA cover the tensor-memory round trips and barriers of the other (the tile loop is latency-bound, not issue-bound).
 template <int NB> struct Cfg {
   static constexpr int STAGES = NB == 2 ? 4 : 2;
-  static constexpr int OFF_Q = STAGES * STAGE_BYTES;       // Q_hi | Q_lo: 128 rows x 128 B each, SWIZZLE_128B K-major
-  static constexpr int OFF_CTRL = OFF_Q + 2 * QTILE;
+  static constexpr int OFF_CTRL = STAGES * STAGE_BYTES;
   static constexpr int SMEM = OFF_CTRL + 3072 + 1024;      // barriers / exchange + alignment slack
-  static constexpr int TM_S = 0, TM_O = 64 * NB, TM_P = TM_O + 64;
+  static constexpr int TM_S = 0, TM_O = 64 * NB, TM_P = TM_O + 64, TM_Q = TM_P + 64 * NB;
   static constexpr int TM_COLS = NB == 2 ? 512 : 256;
 };
 constexpr int THREADS = 64 + 256;                   // TMA, MMA, 8 softmax warps
-constexpr uint32_t IDESC_S = idesc_f16(128, 64, false, false);                      // A (Q) and B (K): K-major smem
+constexpr uint32_t IDESC_S = idesc_f16(128, 64, false, false);                      // A: TMEM, B: K-major smem
 constexpr uint32_t IDESC_PV = idesc_f16(128, 64, false, false) | (1u << 16);        // B (= V tile) is MN-major
 
 struct Args {
+  const uint16_t* q_hi; const uint16_t* q_lo; int ldq;     // q planes (token-major, head h at columns 64 h)
   const float* vinv;                                       // [heads][rows] inverse scales of the v rows
   long long rows;                                          // n_seq * N
   float* o; uint16_t* o_hi; uint16_t* o_lo; int ldo;
@@ -83,11 +83,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* u) {
 
 template <int NB>
 __global__ void __launch_bounds__(THREADS, 3 - NB)
-attn_f16_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
-                const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+attn_f16_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                 const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl, const Args a) {
   constexpr int STAGES = Cfg<NB>::STAGES, OFF_CTRL = Cfg<NB>::OFF_CTRL;
-  constexpr int TM_S = Cfg<NB>::TM_S, TM_O = Cfg<NB>::TM_O, TM_P = Cfg<NB>::TM_P, OFF_Q = Cfg<NB>::OFF_Q;
+  constexpr int TM_S = Cfg<NB>::TM_S, TM_O = Cfg<NB>::TM_O, TM_P = Cfg<NB>::TM_P, TM_Q = Cfg<NB>::TM_Q;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTRL);
@@ -109,8 +108,6 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   const int col0 = head * D;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQh)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQl)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKl)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmVh)) : "memory");
@@ -121,7 +118,7 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
       mbar_init(&o_full[i], 1);
       mbar_init(&p_full[i], 8);
     }
-    mbar_init(&q_ready, 1);
+    mbar_init(&q_ready, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -137,9 +134,6 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      mbar_expect_tx(&q_ready, 2 * QTILE);
-      tma_load_2d(&tmQh, &q_ready, smem + OFF_Q, col0, row_q0);
-      tma_load_2d(&tmQl, &q_ready, smem + OFF_Q + QTILE, col0, row_q0);
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % STAGES;
         const uint32_t ph = (j / STAGES) & 1;
@@ -158,7 +152,7 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp converged; one elected lane issues) =================
     const uint32_t sb = smem_u32(smem);
-    const uint64_t q_hi = desc_kmajor(sb + OFF_Q), q_lo = desc_kmajor(sb + OFF_Q + QTILE);
+    const uint32_t tq_hi = tmem_base + TM_Q, tq_lo = tmem_base + TM_Q + 32;
     auto issue_s = [&](int j) {
       const int s = j % STAGES, b = j % NB;
       mbar_wait(&full[s], (j / STAGES) & 1);
@@ -168,11 +162,11 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
         const uint32_t d = tmem_base + TM_S + b * 64;
         const uint64_t kh = desc_kmajor(sb + s * STAGE_BYTES), kl = desc_kmajor(sb + s * STAGE_BYTES + TILE);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {           // 16 of the 64 head dims per MMA (32 bytes along the swizzled 128-byte rows)
+        for (int kk = 0; kk < 4; ++kk) {           // 16 of the 64 head dims per MMA (8 TMEM columns of packed fp16 pairs)
           const uint64_t adv = (uint64_t)(kk * 32 >> 4);
-          mma_f16(d, q_lo + adv, kh + adv, IDESC_S, kk != 0);
-          mma_f16(d, q_hi + adv, kl + adv, IDESC_S, 1);
-          mma_f16(d, q_hi + adv, kh + adv, IDESC_S, 1);
+          mma_f16_ts(d, tq_lo + kk * 8, kh + adv, IDESC_S, kk != 0);
+          mma_f16_ts(d, tq_hi + kk * 8, kl + adv, IDESC_S, 1);
+          mma_f16_ts(d, tq_hi + kk * 8, kh + adv, IDESC_S, 1);
         }
         tc_commit(&s_full[b]);
       }
@@ -212,6 +206,25 @@ attn_f16_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant_
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int bar_id = 2 + q;                        // named barrier of this warp pair (64 threads)
     const int st = threadIdx.x - 64;                 // 0..255 among the softmax threads
+    // ---- Q planes of this row half -> tensor memory (two fp16 per column), straight from global memory
+    {
+      const size_t off = (size_t)(row_q0 + r) * a.ldq + col0 + half * 32;
+      uint32_t h[16], l[16];
+      const uint4* ph = reinterpret_cast<const uint4*>(a.q_hi + off);
+      const uint4* pl = reinterpret_cast<const uint4*>(a.q_lo + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 x = __ldg(ph + i), y = __ldg(pl + i);
+        h[4 * i] = x.x; h[4 * i + 1] = x.y; h[4 * i + 2] = x.z; h[4 * i + 3] = x.w;
+        l[4 * i] = y.x; l[4 * i + 1] = y.y; l[4 * i + 2] = y.z; l[4 * i + 3] = y.w;
+      }
+      tmem_st16(tmem_base + lane_addr + TM_Q + half * 16, h);
+      tmem_st16(tmem_base + lane_addr + TM_Q + 32 + half * 16, l);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_ready);
+    }
     // ---- one power of two for P'' = p * vinv_j: the largest inverse V scale of this sequence and head
     float vmx = 0.f;
     for (int i = st; i < a.N; i += 256) vmx = fmaxf(vmx, __ldg(a.vinv + (size_t)head * a.rows + row_k0 + i));
@@ -329,7 +342,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode2d(CUtensorMap* m, const uint16_t* base, int cols, long long rows, int ld, int box_rows) {
+static int encode2d(CUtensorMap* m, const uint16_t* base, int cols, long long rows, int ld) {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;
@@ -341,7 +354,7 @@ static int encode2d(CUtensorMap* m, const uint16_t* base, int cols, long long ro
   if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return OMT_E_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {64, (cuuint32_t)KT};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -370,14 +383,12 @@ extern "C" int omt_attn_spatial_h(const uint16_t* q_hi, const uint16_t* q_lo, in
   OMT_REQUIRE(heads > 0 && heads <= 65535 && n_seq <= 65535 && qk_plane_scale > 0.f, "omt_attn_spatial_h: bad arguments");
   if (n_seq == 0) return OMT_OK;
   const long long rows = (long long)n_seq * N;
-  CUtensorMap tmQh, tmQl, tmKh, tmKl, tmVh, tmVl;
+  CUtensorMap tmKh, tmKl, tmVh, tmVl;
   int rc;
-  if ((rc = encode2d(&tmQh, q_hi, heads * D, rows, ldq, QT))) return rc;
-  if ((rc = encode2d(&tmQl, q_lo, heads * D, rows, ldq, QT))) return rc;
-  if ((rc = encode2d(&tmKh, k_hi, heads * D, rows, ldk, KT))) return rc;
-  if ((rc = encode2d(&tmKl, k_lo, heads * D, rows, ldk, KT))) return rc;
-  if ((rc = encode2d(&tmVh, v_hi, heads * D, rows, ldv, KT))) return rc;
-  if ((rc = encode2d(&tmVl, v_lo, heads * D, rows, ldv, KT))) return rc;
+  if ((rc = encode2d(&tmKh, k_hi, heads * D, rows, ldk))) return rc;
+  if ((rc = encode2d(&tmKl, k_lo, heads * D, rows, ldk))) return rc;
+  if ((rc = encode2d(&tmVh, v_hi, heads * D, rows, ldv))) return rc;
+  if ((rc = encode2d(&tmVl, v_lo, heads * D, rows, ldv))) return rc;
   static bool attr[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -386,12 +397,12 @@ extern "C" int omt_attn_spatial_h(const uint16_t* q_hi, const uint16_t* q_lo, in
     OMT_CUDA(cudaFuncSetAttribute(attn_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM));
     attr[dev] = true;
   }
-  Args a{vinv, rows, o, o_hi, o_lo, ldo, N, scale * 1.4426950408889634f / qk_plane_scale};
+  Args a{q_hi, q_lo, ldq, vinv, rows, o, o_hi, o_lo, ldo, N, scale * 1.4426950408889634f / qk_plane_scale};
   dim3 grid(N / QT, heads, n_seq);
   if (g_attn_f16_ctas == 2)
-    OMT_CUDA(launch_k(attn_f16_kernel<1>, grid, dim3(THREADS), Cfg<1>::SMEM, (cudaStream_t)stream, tmQh, tmQl, tmKh, tmKl, tmVh, tmVl, a));
+    OMT_CUDA(launch_k(attn_f16_kernel<1>, grid, dim3(THREADS), Cfg<1>::SMEM, (cudaStream_t)stream, tmKh, tmKl, tmVh, tmVl, a));
   else
-    OMT_CUDA(launch_k(attn_f16_kernel<2>, grid, dim3(THREADS), Cfg<2>::SMEM, (cudaStream_t)stream, tmQh, tmQl, tmKh, tmKl, tmVh, tmVl, a));
+    OMT_CUDA(launch_k(attn_f16_kernel<2>, grid, dim3(THREADS), Cfg<2>::SMEM, (cudaStream_t)stream, tmKh, tmKl, tmVh, tmVl, a));
   OMT_LAUNCH_CHECK();
   return OMT_OK;
 }
