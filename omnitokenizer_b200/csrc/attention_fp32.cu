@@ -195,17 +195,18 @@ __global__ void __launch_bounds__(256) attn_temporal_kernel(const float* __restr
   const int n = (int)(bn % N);
   const int b = (int)(bn / N);
   const size_t col = (size_t)head * 64 + 2 * lane;
-  float2 kr[T], vr[T];
+  float2 kr[T], vr[T], qr[T];           // all 3 T loads of the sequence are in flight before the first use
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const size_t row = ((size_t)b * T + t) * N + n;
     kr[t] = *reinterpret_cast<const float2*>(k + row * ldk + col);
     vr[t] = *reinterpret_cast<const float2*>(v + row * ldv + col);
+    qr[t] = *reinterpret_cast<const float2*>(q + row * ldq + col);
   }
 #pragma unroll
   for (int i = 0; i < T; ++i) {
     const size_t row = ((size_t)b * T + i) * N + n;
-    const float2 qv = *reinterpret_cast<const float2*>(q + row * ldq + col);
+    const float2 qv = qr[i];
     float s[T];
 #pragma unroll
     for (int j = 0; j < T; ++j) s[j] = qv.x * kr[j].x + qv.y * kr[j].y;

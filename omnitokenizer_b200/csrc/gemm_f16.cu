@@ -257,12 +257,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       };
       if (EPI == OMT_EPI_NONE && BN == 128) load_res(0);      // 64 accumulator registers: room to prefetch
 
-      // ---- drain: this lane's row of both accumulators -> registers (main + cross * 2^-11), then release the buffer
+      // ---- drain: this lane's row of both accumulators -> registers (main + cross * 2^-11), then release the buffer.
+      //      The q / k / v epilogues drain one 64-column head at a time (their shared-memory / TMA stores are ordered with
+      //      the release, so draining everything first keeps all 128 values of the row live and spills); the others drain
+      //      all chunks, release, and let the compiler interleave the arithmetic.
       float v[CH][32];
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
+      auto drain = [&](int c) {
         if (NACC == 2) {
           float x[32];
           tmem_ld32(t_main + (uint32_t)(BN + c * 32), x);
@@ -271,13 +273,27 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           for (int j = 0; j < 32; ++j) v[c][j] = fmaf(x[j], 1.0f / F16X3_LO_SCALE, v[c][j]);
         } else {
           tmem_ld32(t_main + (uint32_t)(c * 32), v[c]);
+          const float2 os2 = make_float2(out_scale, out_scale);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[c][j] *= out_scale;
+          for (int j = 0; j < 32; j += 2) {
+            const float2 t = fmul2(make_float2(v[c][j], v[c][j + 1]), os2);
+            v[c][j] = t.x; v[c][j + 1] = t.y;
+          }
         }
+      };
+      auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(mapa(smem_u32(&tmem_empty[acc]), 0));
+      };
+      constexpr bool PER_HEAD = (EPI == OMT_EPI_QKV || EPI == OMT_EPI_QKV_PLANES);
+      // plain epilogue with two accumulator buffers: the release is not urgent, drain chunk by chunk (no spills)
+      constexpr bool PER_CHUNK = (EPI == OMT_EPI_NONE && NBUF == 2 && BN == 256);
+      if constexpr (!PER_HEAD && !PER_CHUNK) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) drain(c);
+        release();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(mapa(smem_u32(&tmem_empty[acc]), 0));
 
       // stage a finished 32 x 32 fp32 box in the slab (swizzled, conflict-free 16-byte stores) and hand it to the TMA
       auto store_box = [&](int n, const float (&t)[32]) {
@@ -315,6 +331,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #pragma unroll
         for (int hd = 0; hd < CH / 2; ++hd) {
           const int nh = n0 + hd * 64;
+          drain(2 * hd);
+          drain(2 * hd + 1);
+          if (hd == CH / 2 - 1) release();
           if (nh < g.N) {
             float (&va)[32] = v[2 * hd];
             float (&vb)[32] = v[2 * hd + 1];
@@ -346,26 +365,29 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                   }
                 }
               }
-              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              // sum of squares and inv * scale on packed pairs (FFMA2 / FMUL2: half the issue slots of the scalar forms)
+              float2 sq0 = make_float2(0.f, 0.f), sq1 = make_float2(0.f, 0.f);
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                s0 = fmaf(va[j], va[j], s0); s1 = fmaf(va[j + 1], va[j + 1], s1);
-                s2 = fmaf(va[j + 2], va[j + 2], s2); s3 = fmaf(va[j + 3], va[j + 3], s3);
+                const float2 a0 = make_float2(va[j], va[j + 1]), a1 = make_float2(va[j + 2], va[j + 3]);
+                sq0 = ffma2(a0, a0, sq0); sq1 = ffma2(a1, a1, sq1);
               }
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                s0 = fmaf(vb[j], vb[j], s0); s1 = fmaf(vb[j + 1], vb[j + 1], s1);
-                s2 = fmaf(vb[j + 2], vb[j + 2], s2); s3 = fmaf(vb[j + 3], vb[j + 3], s3);
+                const float2 b0 = make_float2(vb[j], vb[j + 1]), b1 = make_float2(vb[j + 2], vb[j + 3]);
+                sq0 = ffma2(b0, b0, sq0); sq1 = ffma2(b1, b1, sq1);
               }
-              const float inv = 1.0f / fmaxf(sqrtf((s0 + s1) + (s2 + s3)), 1e-12f);
+              const float inv = 1.0f / fmaxf(sqrtf((sq0.x + sq0.y) + (sq1.x + sq1.y)), 1e-12f);
+              const float2 inv2 = make_float2(inv, inv);
               const float4* scv = reinterpret_cast<const float4*>((nh < g.qk_cols / 2) ? g.q_scale : g.k_scale);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 sa = __ldg(scv + i), sb = __ldg(scv + 8 + i);
-                va[4 * i] = va[4 * i] * inv * sa.x; va[4 * i + 1] = va[4 * i + 1] * inv * sa.y;
-                va[4 * i + 2] = va[4 * i + 2] * inv * sa.z; va[4 * i + 3] = va[4 * i + 3] * inv * sa.w;
-                vb[4 * i] = vb[4 * i] * inv * sb.x; vb[4 * i + 1] = vb[4 * i + 1] * inv * sb.y;
-                vb[4 * i + 2] = vb[4 * i + 2] * inv * sb.z; vb[4 * i + 3] = vb[4 * i + 3] * inv * sb.w;
+                float2 t;
+                t = fmul2(fmul2(make_float2(va[4 * i], va[4 * i + 1]), inv2), make_float2(sa.x, sa.y)); va[4 * i] = t.x; va[4 * i + 1] = t.y;
+                t = fmul2(fmul2(make_float2(va[4 * i + 2], va[4 * i + 3]), inv2), make_float2(sa.z, sa.w)); va[4 * i + 2] = t.x; va[4 * i + 3] = t.y;
+                t = fmul2(fmul2(make_float2(vb[4 * i], vb[4 * i + 1]), inv2), make_float2(sb.x, sb.y)); vb[4 * i] = t.x; vb[4 * i + 1] = t.y;
+                t = fmul2(fmul2(make_float2(vb[4 * i + 2], vb[4 * i + 3]), inv2), make_float2(sb.z, sb.w)); vb[4 * i + 2] = t.x; vb[4 * i + 3] = t.y;
               }
             }
             if constexpr (EPI == OMT_EPI_QKV) {
@@ -384,10 +406,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                 if (row_ok) g.vinv[(size_t)((nh - g.qk_cols) >> 6) * g.M + m] = inv;
               }
               uint32_t wh[32], wl[32];
+              const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                split2u(va[2 * i] * sc, va[2 * i + 1] * sc, wh[i], wl[i]);
-                split2u(vb[2 * i] * sc, vb[2 * i + 1] * sc, wh[16 + i], wl[16 + i]);
+                split2u_pk(fmul2(make_float2(va[2 * i], va[2 * i + 1]), sc2), wh[i], wl[i]);
+                split2u_pk(fmul2(make_float2(vb[2 * i], vb[2 * i + 1]), sc2), wh[16 + i], wl[16 + i]);
               }
               store_plane(&tmPh, nh, wh);
               store_plane(&tmPl, nh, wl);
@@ -424,6 +447,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const int n = n0 + c * 32;
+          if constexpr (PER_CHUNK) {
+            drain(c);
+            if (c == CH - 1) release();
+          }
           if (n < g.N) {
             if (g.bias != nullptr) {
 #pragma unroll
