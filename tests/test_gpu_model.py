@@ -19,16 +19,16 @@ def _math_modes():
 
 
 VARIANTS = {"base": dict(OMT_ATTN_F16="0", OMT_STATIC_U="0", OMT_PEG_KERNEL="3", OMT_ATTN_CTAS="1"),
-            # the shipped defaults: fp16-plane attention core, cp.async PEG
+            # the shipped defaults: fp16-plane attention core with two CTAs per SM, cp.async PEG, statically scaled GEGLU planes
             "default": dict(),
-            # every optional kernel: statically scaled GEGLU planes (single-accumulator FF2), two attention CTAs per SM
-            "fast": dict(OMT_ATTN_F16="1", OMT_STATIC_U="1", OMT_PEG_KERNEL="4", OMT_ATTN_CTAS="2")}
+            # the alternate shapes of the default kernels: one attention CTA per SM, two-accumulator FF2
+            "alt": dict(OMT_ATTN_F16="1", OMT_STATIC_U="0", OMT_PEG_KERNEL="4", OMT_ATTN_CTAS="1")}
 
 
-@pytest.fixture(autouse=True, params=[v for v in os.environ.get("OMT_TEST_VARIANTS", "base,default,fast").split(",") if v])
+@pytest.fixture(autouse=True, params=[v for v in os.environ.get("OMT_TEST_VARIANTS", "base,default,alt").split(",") if v])
 def _kernel_variant(request, monkeypatch):
-    """every model-level test runs with the conservative kernel set, the shipped defaults and every optional kernel on (the
-    sets only differ in f16x3 math)"""
+    """every model-level test runs with the conservative kernel set, the shipped defaults and the alternate shapes of the default kernels
+    (the sets only differ in f16x3 math)"""
     for k in ("OMT_ATTN_F16", "OMT_STATIC_U", "OMT_PEG_KERNEL", "OMT_ATTN_CTAS"):
         monkeypatch.delenv(k, raising=False)
     for k, v in VARIANTS[request.param].items():
