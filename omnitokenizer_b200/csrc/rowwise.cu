@@ -482,12 +482,15 @@ __device__ __forceinline__ float2 peg_step(float2 (&win)[9][3], const float2 (&w
   return acc;
 }
 
-__global__ void __launch_bounds__(256) peg_tile4_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                        const float* __restrict__ w27,
-                                                        const float* __restrict__ bias, int T, int h, int w,
-                                                        int C, int temporal, int causal, int TT, int HB, int RS) {
+__global__ void __launch_bounds__(160, 3) peg_tile4_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           const float* __restrict__ w27,
+                                                           const float* __restrict__ bias, int T, int h, int w,
+                                                           int C, int temporal, int causal, int TT, int HB, int RS, int zrow) {
   pdl_sync();
-  extern __shared__ __align__(16) float tile[];      // [(TT+2)][(HB+2)] rows of RS floats ((w+2)*16 + pad)
+  // [valid planes of the tile][(HB+2)] rows of RS floats ((w+2)*16 + pad), then ONE all-zero row at index zrow: planes
+  // outside the volume (the causal pad in front, the halo behind the last plane) are not stored -- every window row that
+  // falls into one reads the zero row instead.  5 of 7 planes at T' = 5: 69 KB instead of 94 KB, three CTAs per SM.
+  extern __shared__ __align__(16) float tile[];
   const int N = h * w;
   const int n_hblk = (h + HB - 1) / HB;
   const int t0 = (blockIdx.x / n_hblk) * TT, h0 = (blockIdx.x % n_hblk) * HB;
@@ -499,14 +502,18 @@ __global__ void __launch_bounds__(256) peg_tile4_kernel(const float* __restrict_
   const uint32_t inv_T = (65536u + (uint32_t)T - 1u) / (uint32_t)T;       // floor(v / T) == (v * inv_T) >> 16 for v < 65536 / T
   const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
   const int chunks = (w + 2) * 4;                                          // 16-byte chunks per halo row
+  const int pz_lo = t0 < pad_lo ? pad_lo - t0 : 0;                         // leading planes of the tile that lie before t = 0
+  for (int i = threadIdx.x; i < RS / 4; i += blockDim.x)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(tile_s + (uint32_t)(zrow * RS + 4 * i) * 4u), "f"(0.f) : "memory");
   // ---- halo tile: warp <-> halo row; lane <-> 16-byte chunk (consecutive lanes write consecutive shared addresses)
   for (int pr = warp; pr < rows; pr += nwarps) {
     const int ph = pr % (HB + 2), pt = pr / (HB + 2);
     const int t2 = t0 - pad_lo + pt, h2 = h0 - 1 + ph;
-    const bool row_ok = t2 >= 0 && t2 < T && h2 >= 0 && h2 < h;
+    if (t2 < 0 || t2 >= T) continue;                                       // plane outside the volume: not stored
+    const bool row_ok = h2 >= 0 && h2 < h;
     const int fb = row_ok ? (t2 * h + h2) * w : 0;                         // volume position of (t2, h2, w2 = 0)
     const int tau0 = fb % T, nn0 = fb / T;
-    const uint32_t dst_row = tile_s + (uint32_t)(pr * RS) * 4u;
+    const uint32_t dst_row = tile_s + (uint32_t)(((pt - pz_lo) * (HB + 2) + ph) * RS) * 4u;
     for (int j = lane; j < chunks; j += 32) {
       const int w2 = (j >> 2) - 1;
       const bool ok = row_ok && w2 >= 0 && w2 < w;
@@ -542,10 +549,12 @@ __global__ void __launch_bounds__(256) peg_tile4_kernel(const float* __restrict_
   if (!active) return;
   // shared byte addresses of halo column 0 of the 9 window rows of this strip
   uint32_t a[9];
-  {
-    const uint32_t base = tile_s + (uint32_t)(((st * (HB + 2) + sh) * RS + 2 * cp) * 4);
 #pragma unroll
-    for (int r9 = 0; r9 < 9; ++r9) a[r9] = base + (uint32_t)((((r9 / 3) * (HB + 2) + r9 % 3) * RS) * 4);
+  for (int r9 = 0; r9 < 9; ++r9) {
+    const int pt = st + r9 / 3;                     // tile plane of this window row
+    const int t2 = t0 - pad_lo + pt;
+    const int prow = (t2 < 0 || t2 >= T) ? zrow : (pt - pz_lo) * (HB + 2) + sh + r9 % 3;
+    a[r9] = tile_s + (uint32_t)((prow * RS + 2 * cp) * 4);
   }
   float2 win[9][3];
 #pragma unroll
@@ -795,12 +804,23 @@ extern "C" int omt_peg_volume(const float* x, float* y, const float* w27, const 
   const bool fast_ok = T <= 64 && w <= 254 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   const bool v4 = g_peg_kernel == 4 && fast_ok;
   if (v4) {
-    static size_t smem4_set = 0;
-    if (smem > smem4_set) {
-      OMT_CUDA(cudaFuncSetAttribute(peg_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem4_set = smem;
+    // planes of a tile that lie inside the volume (the others are one shared zero row): the maximum over the t-blocks
+    const int pad_lo = causal ? 2 : 1;
+    int vp = 1;
+    for (int t0 = 0; t0 < T; t0 += TT) {
+      const int lo = t0 - pad_lo < 0 ? 0 : t0 - pad_lo, hi = t0 - pad_lo + TT + 2 > T ? T : t0 - pad_lo + TT + 2;
+      if (hi - lo > vp) vp = hi - lo;
     }
-    OMT_CUDA(launch_k(peg_tile4_kernel, grid, dim3(threads), smem, (cudaStream_t)stream, x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS));
+    const int zrow = vp * (HB + 2);
+    const size_t smem4 = (size_t)(zrow + 1) * RS * sizeof(float);
+    static size_t smem4_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && smem4 > smem4_set[dev]) {
+      OMT_CUDA(cudaFuncSetAttribute(peg_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+      smem4_set[dev] = smem4;
+    }
+    OMT_CUDA(launch_k(peg_tile4_kernel, grid, dim3(threads), smem4, (cudaStream_t)stream, x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS, zrow));
   } else {
     OMT_CUDA(launch_k(peg_tile_kernel, grid, dim3(threads), smem, (cudaStream_t)stream, x, y, w27, bias, T, h, w, C, temporal, causal, TT, HB, RS));
   }
