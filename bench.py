@@ -175,7 +175,9 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch.multiprocessing as mp
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if os.environ.get("OMT_BENCH_BATCH"):        # diagnostic (same knob as the GPU arm): a smaller batch of the workload
+        wl["shape"] = (int(os.environ["OMT_BENCH_BATCH"]),) + wl["shape"][1:]
     vae = bool(wl.get("vae"))
     m = make_model(torch.device("cpu"), vae)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}

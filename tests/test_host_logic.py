@@ -1,5 +1,6 @@
 """CPU tests of the host-side conventions of OmniTokenizer_VQGAN.decode / encode with a stub engine
 (no kernels run): the index / flat-index / VAE layout rules of omnitokenizer.py:268-317."""
+import os
 import types
 
 import pytest
@@ -110,3 +111,21 @@ def test_f16x3_split_is_tight():
     big = torch.tensor([1e6, -3e5, 65504.0])
     hi, lo = L.split_f16(big)
     assert torch.isfinite(hi.float()).all() and torch.isfinite(lo.float()).all()        # saturates, never inf / nan
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs next to the GPU arm) on a 2-image slice of cfg-2: one JSON line with
+    the contract's keys, the metric / unit / config of the GPU arm, and a cpu_baseline describing the run."""
+    import json, subprocess, sys
+    env = dict(os.environ, OMT_BENCH_BATCH="2", OMT_REF_WORKERS="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--workload", "cfg2", "--steps", "1", "--warmup", "1"],
+                         cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "video_frames_per_sec_encode_decode" and line["unit"] == "frames/s"
+    assert line["higher_is_better"] is True and line["steps"] == 1 and line["n_gpus"] == 1
+    assert line["config"]["global_batch"] == 2 and line["config"]["workload"].startswith("cfg2")
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] > 0 and "full batch" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
