@@ -165,6 +165,16 @@ __device__ __forceinline__ void split2u_pk(float2 v, uint32_t& hi2, uint32_t& lo
   const float2 d = ffma2(unpack_f16x2(hi2), make_float2(-1.f, -1.f), v);      // v - hi, exact
   lo2 = pack_f16x2_sat(d.x, d.y);
 }
+// 8 consecutive row-scaled values -> one 16-byte store per plane
+__device__ __forceinline__ void store_split8u(uint16_t* hi, uint16_t* lo, size_t off, float4 a, float4 b, float scale) {
+  uint4 h, l;
+  split2u(a.x * scale, a.y * scale, h.x, l.x);
+  split2u(a.z * scale, a.w * scale, h.y, l.y);
+  split2u(b.x * scale, b.y * scale, h.z, l.z);
+  split2u(b.z * scale, b.w * scale, h.w, l.w);
+  *reinterpret_cast<uint4*>(hi + off) = h;
+  *reinterpret_cast<uint4*>(lo + off) = l;
+}
 __device__ __forceinline__ float max4abs(float4 v) { return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))); }
 
 __device__ __forceinline__ float gelu_erf(float x) {

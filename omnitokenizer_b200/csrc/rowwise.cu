@@ -53,7 +53,9 @@ struct LnPlanes {          // optional fp16 hi / lo operand planes (omt_layernor
   float* y_rs; float* x_rs;          // non-NULL: row-scaled planes (omt_common.cuh), the inverse row scale goes here
 };
 
-template <int NV>   // float4 chunks per lane
+// PAIR (C a multiple of 256, NV even): a lane owns 8 consecutive columns per 256-column block (two adjacent float4 chunks), so
+// the row-scaled planes leave as 16-byte stores (512 B per warp instruction) instead of 8-byte ones.
+template <int NV, bool PAIR>   // float4 chunks per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx,
                                                         float* __restrict__ y, int ldy,
                                                         const float* __restrict__ w,
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
+    const int c = PAIR ? ((i >> 1) * 32 + lane) * 8 + (i & 1) * 4 : (i * 32 + lane) * 4;
     if (c < C) {
       v[i] = *reinterpret_cast<const float4*>(xr + c);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -85,10 +87,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     for (int i = 0; i < NV; ++i) mx = fmaxf(mx, max4abs(v[i]));
     float sc, inv;
     row_scale(warp_max(mx), sc, inv);
+    if constexpr (PAIR) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < C) store_split4u(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i], sc);
+      for (int i = 0; i < NV; i += 2) {
+        const int c = ((i >> 1) * 32 + lane) * 8;
+        if (c < C) store_split8u(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i], v[i + 1], sc);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < C) store_split4u(pl.x_hi, pl.x_lo, (size_t)lrow * pl.lds + c, v[i], sc);
+      }
     }
     if (lane == 0) pl.x_rs[lrow] = inv;
   }
@@ -96,7 +106,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
+    const int c = PAIR ? ((i >> 1) * 32 + lane) * 8 + (i & 1) * 4 : (i * 32 + lane) * 4;
     if (c < C) {
       v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
       q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float omx = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
+    const int c = PAIR ? ((i >> 1) * 32 + lane) * 8 + (i & 1) * 4 : (i * 32 + lane) * 4;
     if (c < C) {
       const float4 g = *reinterpret_cast<const float4*>(w + c);
       float4 o;
@@ -126,10 +136,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (pl.y_hi != nullptr && pl.y_rs != nullptr) {      // row-scaled planes of the normalised row
     float sc, inv;
     row_scale(warp_max(omx), sc, inv);
+    if constexpr (PAIR) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < C) store_split4u(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, v[i], sc);
+      for (int i = 0; i < NV; i += 2) {
+        const int c = ((i >> 1) * 32 + lane) * 8;
+        if (c < C) store_split8u(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, v[i], v[i + 1], sc);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < C) store_split4u(pl.y_hi, pl.y_lo, (size_t)lrow * pl.lds + c, v[i], sc);
+      }
     }
     if (lane == 0) pl.y_rs[lrow] = inv;
   }
@@ -665,13 +683,22 @@ static int layernorm_impl(const char* who, const float* x, int ldx, float* y, in
   if (M == 0) return OMT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int nv = (C / 4 + 31) / 32;
+  // 8 consecutive columns per lane (16-byte plane stores) when the row splits into whole 256-column blocks and the planes allow it
+  const bool pair = C % 256 == 0 && pl.lds % 8 == 0 &&
+                    ((uintptr_t)pl.y_hi | (uintptr_t)pl.y_lo | (uintptr_t)pl.x_hi | (uintptr_t)pl.x_lo) % 16 == 0;
   dim3 grid((M + 7) / 8), block(256);
   switch (nv) {
-    case 1: OMT_CUDA(launch_k(layernorm_kernel<1>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
-    case 2: OMT_CUDA(launch_k(layernorm_kernel<2>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
-    case 3: OMT_CUDA(launch_k(layernorm_kernel<3>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
-    case 4: OMT_CUDA(launch_k(layernorm_kernel<4>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
-    default: OMT_CUDA(launch_k(layernorm_kernel<8>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
+    case 1: OMT_CUDA(launch_k(layernorm_kernel<1, false>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
+    case 2:
+      if (pair) OMT_CUDA(launch_k(layernorm_kernel<2, true>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl));
+      else OMT_CUDA(launch_k(layernorm_kernel<2, false>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl));
+      break;
+    case 3: OMT_CUDA(launch_k(layernorm_kernel<3, false>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
+    case 4:
+      if (pair) OMT_CUDA(launch_k(layernorm_kernel<4, true>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl));
+      else OMT_CUDA(launch_k(layernorm_kernel<4, false>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl));
+      break;
+    default: OMT_CUDA(launch_k(layernorm_kernel<8, false>, grid, block, 0, st, x, ldx, y, ldy, w, b, M, C, eps, seg, seg_stride, seg_off, pl)); break;
   }
   OMT_LAUNCH_CHECK();
   return OMT_OK;
