@@ -15,8 +15,9 @@
 //     canonical SWIZZLE_128B MN-major layout, so nothing is transposed anywhere.
 //   * the per-key inverse V scale is folded into P: P'' = p * vinv_j * 2^ep with ONE power of two per CTA taken from the
 //     largest vinv of the sequence, so p'' stays in fp16 range; 2^-ep comes off with the final 1 / row-sum.
-//   TMEM columns: S[2] 0-127 | O 128-191 (accumulates over the key tiles) | P[2] x (hi 32 | lo 32) 256-383 | Q (hi 32 | lo 32) 384-447
-//   smem stage  : K_hi | K_lo | V_hi | V_lo (8 KiB each) | vinv (256 B), 4 stages, every tile one TMA transaction set
+//   TMEM columns (NB = 2): S[2] 0-127 | O 128-191 (accumulates over the key tiles) | P[2] x (hi 32 | lo 32) 192-319 | Q (hi 32 | lo 32) 320-383
+//                (NB = 1): S 0-63 | O 64-127 | P 128-191 | Q 192-255
+//   smem stage  : K_hi | K_lo | V_hi | V_lo (8 KiB each) | vinv (256 B), 4 (NB = 2) or 2 (NB = 1) stages, every tile one TMA transaction set
 // Measured alternatives (same box, same process, `scripts/bench_attn.py`, cfg-3 shape, two CTAs per SM): Q as a shared-memory
 // operand (SS-form S MMAs) 299 us vs 288 us for this form; P_hi.[V_hi | V_lo] as one N = 128 MMA: no gain with one CTA per SM and
 // 2.7x slower with two.  The tile loop is bound by the serial chain S read-back -> max -> exp -> P write of the softmax threads,
