@@ -792,11 +792,13 @@ extern "C" int omt_peg(const float* x, float* y, const float* w27, const float* 
   OMT_REQUIRE(C % 4 == 0 && C / 4 <= 128, "omt_peg: C=%d unsupported (need C %% 4 == 0, C <= 512)", C);
   const long long M = (long long)B * rows_per_b;
   if (M == 0) return OMT_OK;
-  static bool attr_set = false;
+  static bool attr_set[64];          // the attribute is per device
   const size_t smem = (size_t)27 * C * sizeof(float);
-  if (!attr_set) {
+  int dev0 = 0;
+  cudaGetDevice(&dev0);
+  if (dev0 >= 0 && dev0 < 64 && !attr_set[dev0]) {
     OMT_CUDA(cudaFuncSetAttribute(peg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 27 * 512 * 4));
-    attr_set = true;
+    attr_set[dev0] = true;
   }
   const unsigned blocks = (unsigned)((M + PEG_ROWS - 1) / PEG_ROWS);
   peg_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(x, y, w27, bias, nbr, rows_per_b, C, M);
@@ -821,10 +823,12 @@ extern "C" int omt_peg_volume(const float* x, float* y, const float* w27, const 
   while (TT > 1 && (smem_of(TT, HB) > 112 * 1024 || TT * HB * 8 > 256)) --TT;
   const size_t smem = smem_of(TT, HB);
   OMT_REQUIRE(smem <= 200 * 1024, "omt_peg_volume: row of %d tokens does not fit the shared-memory tile", w);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  static size_t smem_set[64];        // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && smem > smem_set[dev]) {
     OMT_CUDA(cudaFuncSetAttribute(peg_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+    smem_set[dev] = smem;
   }
   const int threads = ((TT * HB * 8 + 31) / 32) * 32;
   dim3 grid(((T + TT - 1) / TT) * ((h + HB - 1) / HB), C / PEG_CC, B);
@@ -841,8 +845,6 @@ extern "C" int omt_peg_volume(const float* x, float* y, const float* w27, const 
     const int zrow = vp * (HB + 2);
     const size_t smem4 = (size_t)(zrow + 1) * RS * sizeof(float);
     static size_t smem4_set[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && smem4 > smem4_set[dev]) {
       OMT_CUDA(cudaFuncSetAttribute(peg_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
       smem4_set[dev] = smem4;

@@ -333,10 +333,12 @@ extern "C" int omt_pre_vq(const float* x, int ldx, const float* Wt, const float*
   if (cd == 8) {
     OMT_CUDA(launch_k(pre_vq_kernel<8>, dim3(blocks), dim3(256), smem, st, x, ldx, Wt, b, z, M, C, l2));
   } else {
-    static bool set16 = false;
-    if (!set16) {
+    static bool set16[64];           // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !set16[dev]) {
       OMT_CUDA(cudaFuncSetAttribute(pre_vq_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4));
-      set16 = true;
+      set16[dev] = true;
     }
     OMT_CUDA(launch_k(pre_vq_kernel<16>, dim3(blocks), dim3(256), smem, st, x, ldx, Wt, b, z, M, C, l2));
   }
