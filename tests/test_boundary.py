@@ -136,3 +136,20 @@ def test_weight_packing():
     assert p.shape == (16, 4) and torch.equal(p[0], w1[0]) and torch.equal(p[1], w1[5]) and torch.equal(p[9], w1[9])
     assert torch.count_nonzero(p[10:]) == 0
     assert L.pad_rows(torch.ones(130, 4), 128).shape == (256, 4)
+
+
+def test_kernel_selectors_are_documented_and_defaults_match_the_library():
+    """Every omt_set_option selector the Python side knows (DEFAULT_OPTIONS) is described in the public header, and its Python
+    default equals the default compiled into the library sources (the header states the default as `"name" = <value>`)."""
+    import re
+    from omnitokenizer_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "omnitok_b200.h")).read()
+    for name, value in _cabi.DEFAULT_OPTIONS.items():
+        m = re.search(r'"%s" = (\d+) \(default' % re.escape(name), hdr)
+        assert m is not None, f"{name} is not documented with its default in include/omnitok_b200.h"
+        assert int(m.group(1)) == value, f"{name}: header says {m.group(1)}, _cabi.DEFAULT_OPTIONS says {value}"
+    src = "".join(open(os.path.join(root, "omnitokenizer_b200", "csrc", f)).read() for f in ("rowwise.cu", "attention_fp32.cu", "attention_f16.cu", "gemm_f16.cu"))
+    for name, var in (("peg_kernel", "g_peg_kernel"), ("attn_kernel", "g_attn_kernel"), ("attn_f16_ctas", "g_attn_f16_ctas"), ("f16_bn", "g_f16_bn")):
+        m = re.search(r"int %s = (\d+);" % var, src)
+        assert m is not None and int(m.group(1)) == _cabi.DEFAULT_OPTIONS[name], (name, m and m.group(1))
